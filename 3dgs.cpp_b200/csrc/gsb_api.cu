@@ -1,0 +1,730 @@
+// gsb_api.cu -- the C ABI of libgsb200.so (include/gs_b200.h): context, scene upload, frame
+// orchestration.  This is the dispatch glue that replaces Renderer::draw / record*CommandBuffer /
+// create*Pipeline (src/Renderer.cpp:166-364,366-426,468-717): stream ordering instead of
+// pipeline barriers, kernel arguments instead of descriptor sets, and no mid-frame host sync.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "gsb_internal.cuh"
+
+using namespace gsb;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+}  // namespace
+
+struct gsb_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // scene
+    uint64_t n = 0;
+    float4* pos_op = nullptr;
+    float4* cov_a = nullptr;
+    float2* cov_b = nullptr;
+    float* sh = nullptr;
+
+    // frame state
+    Control* ctl = nullptr;
+    Control* ctl_host = nullptr;  // pinned mirror, filled at the end of each frame
+    unsigned long long* pre_status = nullptr;
+    float4* recs = nullptr;
+    uint64_t capacity = 0;
+    unsigned long long* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    unsigned long long* sort_status = nullptr;
+    uint32_t sort_status_tiles = 0;
+    uint32_t epoch = 8;
+    uint2* ranges = nullptr;
+    uint32_t ranges_tiles = 0;
+    void* fb = nullptr;
+    size_t fb_bytes = 0;
+
+    int mode = GSB_MODE_EXACT;
+    bool debug = false;
+    bool timers = true;
+    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_sort[9] = {};  // after hist, after each pass
+    cudaEvent_t ev_done = nullptr;
+    bool frame_pending = false;
+    bool have_frame = false;
+    uint32_t m_hint = 0;
+    uint32_t regrow_count = 0;
+
+    // description of the last frame (for stats / debug download)
+    uint32_t last_w = 0, last_h = 0, last_tiles_x = 0, last_tiles_y = 0, last_passes = 0, last_final = 0;
+
+    // debug copies
+    uint32_t* dbg_tiles = nullptr;
+    uint32_t* dbg_scan = nullptr;
+    uint4* dbg_aabb = nullptr;
+    unsigned long long* dbg_keys_unsorted = nullptr;
+    uint32_t* dbg_vals_unsorted = nullptr;
+    uint64_t dbg_m = 0;
+};
+
+namespace {
+
+int fail(gsb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? GSB_ERR_OOM : GSB_ERR_CUDA, #call, e_); \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int free_arena(gsb_ctx* ctx) {
+    dev_free(ctx->keys[0]);
+    dev_free(ctx->keys[1]);
+    dev_free(ctx->vals[0]);
+    dev_free(ctx->vals[1]);
+    dev_free(ctx->sort_status);
+    ctx->capacity = 0;
+    ctx->sort_status_tiles = 0;
+    return GSB_OK;
+}
+
+int ensure_arena(gsb_ctx* ctx, uint64_t capacity) {
+    if (capacity <= ctx->capacity) return GSB_OK;
+    if (capacity >= (1ull << 30)) return fail(ctx, GSB_ERR_OVERFLOW, "instance arena limited to 2^30 - 1 entries");
+    free_arena(ctx);
+    CK(dev_alloc(&ctx->keys[0], capacity));
+    CK(dev_alloc(&ctx->keys[1], capacity));
+    CK(dev_alloc(&ctx->vals[0], capacity));
+    CK(dev_alloc(&ctx->vals[1], capacity));
+    const uint32_t tiles = (uint32_t)((capacity + sort_tile_items() - 1) / sort_tile_items());
+    CK(dev_alloc(&ctx->sort_status, (size_t)tiles * 256));
+    CK(cudaMemset(ctx->sort_status, 0, (size_t)tiles * 256 * sizeof(unsigned long long)));
+    ctx->sort_status_tiles = tiles;
+    ctx->capacity = capacity;
+    return GSB_OK;
+}
+
+uint32_t bits_for(uint32_t count) {  // bits needed to represent 0 .. count-1
+    uint32_t b = 0;
+    while (b < 32 && (1ull << b) < count) b++;
+    return b;
+}
+
+size_t bytes_per_pixel(int fmt) { return fmt == GSB_FORMAT_RGBA32F ? 16 : 4; }
+
+int wait_frame(gsb_ctx* ctx) {
+    if (ctx->frame_pending) {
+        CK(cudaEventSynchronize(ctx->ev_done));
+        ctx->frame_pending = false;
+        ctx->m_hint = ctx->ctl_host->num_instances;
+    }
+    return GSB_OK;
+}
+
+// Enqueue one frame on `stream`; out_dev is device memory.
+int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out_dev, size_t pitch, int fmt,
+                  cudaStream_t stream) {
+    const uint32_t W = ubo->width, H = ubo->height;
+    const uint32_t tiles_x = (W + GSB_TILE - 1) / GSB_TILE, tiles_y = (H + GSB_TILE - 1) / GSB_TILE;
+    const uint32_t T = tiles_x * tiles_y;
+    if (T > ctx->ranges_tiles) {
+        dev_free(ctx->ranges);
+        CK(dev_alloc(&ctx->ranges, T));
+        ctx->ranges_tiles = T;
+    }
+    const uint32_t n = (uint32_t)ctx->n;
+    const uint32_t chunks = (n + 255) / 256;
+
+    CK(cudaMemsetAsync(ctx->ctl, 0, sizeof(Control), stream));
+    CK(cudaMemsetAsync(ctx->pre_status, 0, (size_t)std::max(chunks, 1u) * sizeof(unsigned long long), stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
+
+    PreprocessParams pp{};
+    pp.pos_op = ctx->pos_op;
+    pp.cov_a = ctx->cov_a;
+    pp.cov_b = ctx->cov_b;
+    pp.sh = ctx->sh;
+    pp.n = n;
+    pp.ubo = *ubo;
+    pp.tile_row_begin = rb;
+    pp.tile_row_end = re;
+    pp.recs = ctx->recs;
+    pp.keys = ctx->keys[0];
+    pp.vals = ctx->vals[0];
+    pp.capacity = (uint32_t)ctx->capacity;
+    pp.status = ctx->pre_status;
+    pp.ctl = ctx->ctl;
+    pp.dbg_tiles = ctx->dbg_tiles;
+    pp.dbg_scan = ctx->dbg_scan;
+    pp.dbg_aabb = ctx->dbg_aabb;
+    CK(launch_preprocess(pp, ctx->debug, stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[1], stream));
+
+    if (ctx->debug) {  // keep the unsorted keys (sortK/VBufferEven right after preprocess_sort)
+        CK(cudaStreamSynchronize(stream));
+        uint32_t m = 0;
+        CK(cudaMemcpy(&m, &ctx->ctl->num_instances, sizeof m, cudaMemcpyDeviceToHost));
+        dev_free(ctx->dbg_keys_unsorted);
+        dev_free(ctx->dbg_vals_unsorted);
+        CK(dev_alloc(&ctx->dbg_keys_unsorted, m));
+        CK(dev_alloc(&ctx->dbg_vals_unsorted, m));
+        CK(cudaMemcpyAsync(ctx->dbg_keys_unsorted, ctx->keys[0], (size_t)m * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(ctx->dbg_vals_unsorted, ctx->vals[0], (size_t)m * 4, cudaMemcpyDeviceToDevice, stream));
+        ctx->dbg_m = m;
+    }
+
+    SortParams sp{};
+    sp.keys[0] = ctx->keys[0];
+    sp.keys[1] = ctx->keys[1];
+    sp.vals[0] = ctx->vals[0];
+    sp.vals[1] = ctx->vals[1];
+    sp.d_m = &ctx->ctl->num_instances;
+    sp.m_hint = ctx->m_hint ? ctx->m_hint : (uint32_t)std::min<uint64_t>(ctx->capacity, 4u * 1024 * 1024);
+    sp.key_bits = 32 + bits_for(T);
+    sp.status = ctx->sort_status;
+    sp.status_tiles = ctx->sort_status_tiles;
+    sp.epoch_base = ctx->epoch;
+    ctx->epoch += 8;
+    if (ctx->epoch >= 0xfffffff0u) {  // epoch wrap: clear the tags once
+        CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
+        ctx->epoch = 8;
+    }
+    sp.ctl = ctx->ctl;
+    sp.num_sms = ctx->num_sms;
+    sp.events = ctx->timers ? ctx->ev_sort : nullptr;
+    uint32_t passes = 0;
+    CK(launch_sort(sp, &passes, stream));
+    const int fin = passes & 1;
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[2], stream));
+
+    CK(launch_tile_ranges(ctx->keys[fin], sp.d_m, sp.m_hint, ctx->ranges, T, ctx->num_sms, stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[3], stream));
+
+    BlendParams bp{};
+    bp.recs = ctx->recs;
+    bp.vals = ctx->vals[fin];
+    bp.ranges = ctx->ranges;
+    bp.width = W;
+    bp.height = H;
+    bp.tiles_x = tiles_x;
+    bp.tile_row_begin = rb;
+    bp.tile_row_end = re;
+    bp.out = out_dev;
+    bp.row_pitch_bytes = pitch;
+    bp.format = fmt;
+    bp.mode = ctx->mode;
+    bp.ctl = ctx->ctl;
+    CK(launch_blend(bp, stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[4], stream));
+
+    CK(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, offsetof(Control, hist), cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(ctx->ev_done, stream));
+    ctx->frame_pending = true;
+    ctx->have_frame = true;
+    ctx->last_w = W;
+    ctx->last_h = H;
+    ctx->last_tiles_x = tiles_x;
+    ctx->last_tiles_y = tiles_y;
+    ctx->last_passes = passes;
+    ctx->last_final = (uint32_t)fin;
+    return GSB_OK;
+}
+
+int check_render_args(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t& rb, uint32_t& re, const void* out, size_t& pitch,
+                      int fmt) {
+    if (!ctx) return GSB_ERR_INVALID;
+    if (!ubo || !out) return fail(ctx, GSB_ERR_INVALID, "null argument");
+    if (!ctx->pos_op) return fail(ctx, GSB_ERR_NO_SCENE, "no scene uploaded");
+    if (fmt < GSB_FORMAT_RGBA32F || fmt > GSB_FORMAT_BGRA8) return fail(ctx, GSB_ERR_INVALID, "bad format");
+    const uint32_t W = ubo->width, H = ubo->height;
+    if (W == 0 || H == 0 || W > 16u * 65535u || H > 16u * 65535u) return fail(ctx, GSB_ERR_INVALID, "bad image size");
+    const uint32_t tiles_y = (H + GSB_TILE - 1) / GSB_TILE;
+    if (re > tiles_y) re = tiles_y;
+    if (rb >= re) return fail(ctx, GSB_ERR_INVALID, "empty tile-row band");
+    const size_t tight = (size_t)W * bytes_per_pixel(fmt);
+    if (pitch == 0) pitch = tight;
+    if (pitch < tight || (pitch % (fmt == GSB_FORMAT_RGBA32F ? 16 : 4)) != 0) return fail(ctx, GSB_ERR_INVALID, "bad row pitch");
+    return GSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsb_abi_version(void) { return GSB_ABI_VERSION; }
+
+int gsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* gsb_last_error(const gsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gsb_create(int device, gsb_ctx** out) {
+    if (!out) return GSB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        g_create_error = "no usable CUDA device (libgsb200 has no CPU path)";
+        if (e != cudaSuccess) g_create_error += std::string(": ") + cudaGetErrorString(e);
+        return GSB_ERR_NO_DEVICE;
+    }
+    gsb_ctx* ctx = new (std::nothrow) gsb_ctx();
+    if (!ctx) return GSB_ERR_OOM;
+    ctx->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        gsb_destroy(ctx);
+        return GSB_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        g_create_error = "libgsb200 is built for sm_100a (B200) only";
+        gsb_destroy(ctx);
+        return GSB_ERR_NO_DEVICE;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = dev_alloc(&ctx->ctl, 1)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->ctl_host), sizeof(Control))) != cudaSuccess) return bail("cudaMallocHost", e);
+    memset(ctx->ctl_host, 0, sizeof(Control));
+    for (auto& ev : ctx->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (auto& ev : ctx->ev_sort)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    *out = ctx;
+    return GSB_OK;
+}
+
+void gsb_destroy(gsb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
+    dev_free(ctx->pos_op);
+    dev_free(ctx->cov_a);
+    dev_free(ctx->cov_b);
+    dev_free(ctx->sh);
+    dev_free(ctx->ctl);
+    if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
+    dev_free(ctx->pre_status);
+    dev_free(ctx->recs);
+    free_arena(ctx);
+    dev_free(ctx->ranges);
+    if (ctx->fb) cudaFree(ctx->fb);
+    dev_free(ctx->dbg_tiles);
+    dev_free(ctx->dbg_scan);
+    dev_free(ctx->dbg_aabb);
+    dev_free(ctx->dbg_keys_unsorted);
+    dev_free(ctx->dbg_vals_unsorted);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_sort)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory mem) {
+    if (!ctx) return GSB_ERR_INVALID;
+    if (n && !vertices) return fail(ctx, GSB_ERR_INVALID, "null vertices");
+    if (n >= (1ull << 30)) return fail(ctx, GSB_ERR_INVALID, "scene limited to 2^30 - 1 Gaussians");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->frame_pending = false;
+    ctx->have_frame = false;
+    dev_free(ctx->pos_op);
+    dev_free(ctx->cov_a);
+    dev_free(ctx->cov_b);
+    dev_free(ctx->sh);
+    dev_free(ctx->recs);
+    dev_free(ctx->pre_status);
+    dev_free(ctx->dbg_tiles);
+    dev_free(ctx->dbg_scan);
+    dev_free(ctx->dbg_aabb);
+    ctx->n = 0;
+    CK(dev_alloc(&ctx->pos_op, n));
+    CK(dev_alloc(&ctx->cov_a, n));
+    CK(dev_alloc(&ctx->cov_b, n));
+    CK(dev_alloc(&ctx->sh, n * 48));
+    CK(dev_alloc(&ctx->recs, n * 3));
+    CK(dev_alloc(&ctx->pre_status, (n + 255) / 256));
+    if (ctx->debug) {
+        CK(dev_alloc(&ctx->dbg_tiles, n));
+        CK(dev_alloc(&ctx->dbg_scan, n));
+        CK(dev_alloc(&ctx->dbg_aabb, n));
+    }
+    // stream the AoS records through a bounded staging buffer (C5: 50 M x 240 B = 12 GB on the host)
+    const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), 1u << 20);
+    float* staging = nullptr;
+    if (mem == GSB_MEM_HOST) CK(dev_alloc(&staging, chunk * 60));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t cnt = std::min(chunk, n - off);
+        const float* src = vertices + off * 60;
+        if (mem == GSB_MEM_HOST) {
+            cudaError_t e = cudaMemcpyAsync(staging, src, cnt * 60 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) {
+                cudaFree(staging);
+                return fail(ctx, GSB_ERR_CUDA, "scene H2D copy", e);
+            }
+            src = staging;
+        }
+        // scale_factor = 1.0f: GSScene.cpp:176
+        cudaError_t e = launch_cov3d(src, cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream);
+        if (e == cudaSuccess && mem == GSB_MEM_HOST) e = cudaStreamSynchronize(ctx->stream);  // staging reuse
+        if (e != cudaSuccess) {
+            if (staging) cudaFree(staging);
+            return fail(ctx, GSB_ERR_CUDA, "cov3d precompute", e);
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (staging) cudaFree(staging);
+    ctx->n = n;
+    ctx->m_hint = 0;
+    // the reference starts the sort arena at N entries (sortBufferSizeMultiplier = 1, Renderer.cpp:235-242)
+    if (ctx->capacity == 0) {
+        int rc = ensure_arena(ctx, std::max<uint64_t>(n, 1024));
+        if (rc != GSB_OK) return rc;
+    }
+    return GSB_OK;
+}
+
+uint64_t gsb_scene_size(const gsb_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+int gsb_set_mode(gsb_ctx* ctx, gsb_mode mode) {
+    if (!ctx || (mode != GSB_MODE_EXACT && mode != GSB_MODE_FAST)) return GSB_ERR_INVALID;
+    ctx->mode = mode;
+    return GSB_OK;
+}
+
+int gsb_set_debug(gsb_ctx* ctx, int debug) {
+    if (!ctx) return GSB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->debug = debug != 0;
+    if (ctx->debug && ctx->n && !ctx->dbg_tiles) {
+        CK(dev_alloc(&ctx->dbg_tiles, ctx->n));
+        CK(dev_alloc(&ctx->dbg_scan, ctx->n));
+        CK(dev_alloc(&ctx->dbg_aabb, ctx->n));
+    }
+    return GSB_OK;
+}
+
+int gsb_set_timers(gsb_ctx* ctx, int enabled) {
+    if (!ctx) return GSB_ERR_INVALID;
+    ctx->timers = enabled != 0;
+    return GSB_OK;
+}
+
+int gsb_reserve_instances(gsb_ctx* ctx, uint64_t capacity) {
+    if (!ctx) return GSB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = wait_frame(ctx);
+    if (rc != GSB_OK) return rc;
+    return ensure_arena(ctx, capacity);
+}
+
+int gsb_render_async(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out_device, size_t pitch,
+                     gsb_format fmt, void* stream) {
+    int rc = check_render_args(ctx, ubo, rb, re, out_device, pitch, fmt);
+    if (rc != GSB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->frame_pending && cudaEventQuery(ctx->ev_done) == cudaSuccess) {  // opportunistic hint refresh
+        ctx->frame_pending = false;
+        ctx->m_hint = ctx->ctl_host->num_instances;
+    }
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return enqueue_frame(ctx, ubo, rb, re, out_device, pitch, fmt, s);
+}
+
+int gsb_render(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out, size_t pitch, gsb_memory out_mem,
+               gsb_format fmt, void* stream) {
+    int rc = check_render_args(ctx, ubo, rb, re, out, pitch, fmt);
+    if (rc != GSB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    const uint32_t H = ubo->height;
+    const uint32_t rows = std::min(H, re * GSB_TILE) - rb * GSB_TILE;
+    const size_t tight = (size_t)ubo->width * bytes_per_pixel(fmt);
+
+    void* dev_out = out;
+    size_t dev_pitch = pitch;
+    if (out_mem == GSB_MEM_HOST) {
+        const size_t need = tight * rows;
+        if (need > ctx->fb_bytes) {
+            if (ctx->fb) cudaFree(ctx->fb);
+            ctx->fb = nullptr;
+            ctx->fb_bytes = 0;
+            CK(cudaMalloc(&ctx->fb, need));
+            ctx->fb_bytes = need;
+        }
+        dev_out = ctx->fb;
+        dev_pitch = tight;
+    }
+    for (int attempt = 0;; attempt++) {
+        rc = enqueue_frame(ctx, ubo, rb, re, dev_out, dev_pitch, fmt, s);
+        if (rc != GSB_OK) return rc;
+        rc = wait_frame(ctx);
+        if (rc != GSB_OK) return rc;
+        if (!ctx->ctl_host->overflow) break;
+        // arena overflow: grow like the reference's sortBufferSizeMultiplier retry (Renderer.cpp:541-563)
+        if (attempt >= 3) return fail(ctx, GSB_ERR_OVERFLOW, "instance arena overflow persists after regrow");
+        const uint64_t want = ctx->ctl_host->instances_total + ctx->ctl_host->instances_total / 4 + 4096;
+        rc = ensure_arena(ctx, want);
+        if (rc != GSB_OK) return rc;
+        ctx->regrow_count++;
+    }
+    if (out_mem == GSB_MEM_HOST) {
+        CK(cudaMemcpy2DAsync(out, pitch, dev_out, dev_pitch, tight, rows, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return GSB_OK;
+}
+
+int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
+    if (!ctx || !out) return GSB_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    if (!ctx->have_frame) return fail(ctx, GSB_ERR_INVALID, "no frame rendered yet");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->frame_pending) {
+        int rc = wait_frame(ctx);
+        if (rc != GSB_OK) return rc;
+    } else {
+        CK(cudaEventSynchronize(ctx->ev_done));
+    }
+    const Control* c = ctx->ctl_host;
+    out->num_gaussians = ctx->n;
+    out->num_visible = c->num_visible;
+    out->num_instances = c->instances_total;
+    out->blend_consumed = c->blend_consumed;
+    out->instance_capacity = ctx->capacity;
+    out->sort_passes = ctx->last_passes;
+    out->regrow_count = ctx->regrow_count;
+    if (ctx->timers) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        out->preprocess_ms = ms;  // fused preprocess + scan + key emission
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+        out->sort_ms = ms;
+        if (ctx->last_passes) {
+            CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev_sort[0]));
+            out->sort_hist_ms = ms;
+            for (uint32_t p = 0; p < ctx->last_passes && p < 8; p++) {
+                CK(cudaEventElapsedTime(&ms, ctx->ev_sort[p], ctx->ev_sort[p + 1]));
+                out->sort_pass_ms[p] = ms;
+            }
+        }
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        out->tile_boundary_ms = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+        out->render_ms = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]));
+        out->frame_ms = ms;
+    }
+    if (c->overflow) return fail(ctx, GSB_ERR_OVERFLOW, "last frame overflowed the instance arena (gsb_render regrows; gsb_render_async does not)");
+    return GSB_OK;
+}
+
+size_t gsb_debug_size(gsb_ctx* ctx, gsb_buffer which) {
+    if (!ctx) return 0;
+    const uint64_t n = ctx->n;
+    if (which == GSB_BUF_COV3D) return (size_t)n * 6 * sizeof(float);
+    if (!ctx->have_frame || !ctx->debug) return 0;
+    if (wait_frame(ctx) != GSB_OK) return 0;
+    const uint64_t m = ctx->ctl_host->num_instances;
+    switch (which) {
+        case GSB_BUF_ATTR: return (size_t)n * sizeof(gsb_vertex_attribute);
+        case GSB_BUF_TILES_OVERLAP:
+        case GSB_BUF_PREFIX_SUM: return (size_t)n * 4;
+        case GSB_BUF_KEYS_UNSORTED:
+        case GSB_BUF_KEYS_SORTED: return (size_t)m * 8;
+        case GSB_BUF_VALS_UNSORTED:
+        case GSB_BUF_VALS_SORTED: return (size_t)m * 4;
+        case GSB_BUF_TILE_BOUNDARY: return (size_t)ctx->last_tiles_x * ctx->last_tiles_y * 8;
+        default: return 0;
+    }
+}
+
+int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) {
+    if (!ctx || !dst) return GSB_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const size_t need = gsb_debug_size(ctx, which);
+    if (need == 0 && which != GSB_BUF_COV3D) return fail(ctx, GSB_ERR_INVALID, "debug buffer unavailable (enable gsb_set_debug before rendering)");
+    if (bytes < need) return fail(ctx, GSB_ERR_INVALID, "destination too small");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaDeviceSynchronize());
+    const uint64_t n = ctx->n;
+    const uint32_t nv = ctx->have_frame ? ctx->ctl_host->num_visible : 0;
+    const uint64_t m = ctx->have_frame ? ctx->ctl_host->num_instances : 0;
+    auto orig_ids = [&](std::vector<uint32_t>& ids) -> int {  // compact id -> original Gaussian index
+        std::vector<float4> recs((size_t)nv * 3);
+        if (nv) CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        ids.resize(nv);
+        for (uint32_t c = 0; c < nv; c++) memcpy(&ids[c], &recs[(size_t)c * 3 + 2].w, 4);
+        return GSB_OK;
+    };
+    switch (which) {
+        case GSB_BUF_COV3D: {
+            std::vector<float4> a(n);
+            std::vector<float2> b(n);
+            if (n) {
+                CK(cudaMemcpy(a.data(), ctx->cov_a, n * sizeof(float4), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(b.data(), ctx->cov_b, n * sizeof(float2), cudaMemcpyDeviceToHost));
+            }
+            float* o = static_cast<float*>(dst);
+            for (uint64_t i = 0; i < n; i++) {
+                o[i * 6 + 0] = a[i].x;
+                o[i * 6 + 1] = a[i].y;
+                o[i * 6 + 2] = a[i].z;
+                o[i * 6 + 3] = a[i].w;
+                o[i * 6 + 4] = b[i].x;
+                o[i * 6 + 5] = b[i].y;
+            }
+            return GSB_OK;
+        }
+        case GSB_BUF_ATTR: {
+            std::vector<float4> recs((size_t)nv * 3);
+            std::vector<uint4> aabb(n);
+            if (nv) CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+            if (n) CK(cudaMemcpy(aabb.data(), ctx->dbg_aabb, n * sizeof(uint4), cudaMemcpyDeviceToHost));
+            gsb_vertex_attribute* o = static_cast<gsb_vertex_attribute*>(dst);
+            memset(o, 0, n * sizeof(gsb_vertex_attribute));
+            for (uint32_t c = 0; c < nv; c++) {
+                const float4 r0 = recs[(size_t)c * 3], r1 = recs[(size_t)c * 3 + 1], r2 = recs[(size_t)c * 3 + 2];
+                uint32_t i;
+                memcpy(&i, &r2.w, 4);
+                if (i >= n) return fail(ctx, GSB_ERR_CUDA, "corrupt compact record");
+                gsb_vertex_attribute& a = o[i];
+                a.conic_opacity[0] = r0.z;
+                a.conic_opacity[1] = r0.w;
+                a.conic_opacity[2] = r1.x;
+                a.conic_opacity[3] = r1.y;
+                a.color_radii[0] = r1.z;
+                a.color_radii[1] = r1.w;
+                a.color_radii[2] = r2.x;
+                a.color_radii[3] = r2.z;
+                a.aabb[0] = aabb[i].x;
+                a.aabb[1] = aabb[i].y;
+                a.aabb[2] = aabb[i].z;
+                a.aabb[3] = aabb[i].w;
+                a.uv[0] = r0.x;
+                a.uv[1] = r0.y;
+                a.depth = r2.y;
+                a.magic = 0x4d415449u;  // common.glsl:14
+            }
+            return GSB_OK;
+        }
+        case GSB_BUF_TILES_OVERLAP:
+            if (n) CK(cudaMemcpy(dst, ctx->dbg_tiles, n * 4, cudaMemcpyDeviceToHost));
+            return GSB_OK;
+        case GSB_BUF_PREFIX_SUM:
+            if (n) CK(cudaMemcpy(dst, ctx->dbg_scan, n * 4, cudaMemcpyDeviceToHost));
+            return GSB_OK;
+        case GSB_BUF_KEYS_UNSORTED:
+            if (m) CK(cudaMemcpy(dst, ctx->dbg_keys_unsorted, m * 8, cudaMemcpyDeviceToHost));
+            return GSB_OK;
+        case GSB_BUF_KEYS_SORTED:
+            if (m) CK(cudaMemcpy(dst, ctx->keys[ctx->last_final], m * 8, cudaMemcpyDeviceToHost));
+            return GSB_OK;
+        case GSB_BUF_VALS_UNSORTED:
+        case GSB_BUF_VALS_SORTED: {
+            std::vector<uint32_t> ids;
+            int rc = orig_ids(ids);
+            if (rc != GSB_OK) return rc;
+            uint32_t* o = static_cast<uint32_t*>(dst);
+            const uint32_t* src = which == GSB_BUF_VALS_UNSORTED ? ctx->dbg_vals_unsorted : ctx->vals[ctx->last_final];
+            if (m) CK(cudaMemcpy(o, src, m * 4, cudaMemcpyDeviceToHost));
+            for (uint64_t k = 0; k < m; k++) {
+                if (o[k] >= nv) return fail(ctx, GSB_ERR_CUDA, "corrupt payload");
+                o[k] = ids[o[k]];
+            }
+            return GSB_OK;
+        }
+        case GSB_BUF_TILE_BOUNDARY:
+            CK(cudaMemcpy(dst, ctx->ranges, need, cudaMemcpyDeviceToHost));
+            return GSB_OK;
+        default: return fail(ctx, GSB_ERR_INVALID, "unknown buffer id");
+    }
+}
+
+int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, uint64_t m,
+                   uint32_t key_bits, void* stream) {
+    if (!ctx) return GSB_ERR_INVALID;
+    if (m == 0) return GSB_OK;
+    if (!keys || !vals || !keys_tmp || !vals_tmp || key_bits == 0 || key_bits > 64) return fail(ctx, GSB_ERR_INVALID, "bad argument");
+    if (m >= (1ull << 30)) return fail(ctx, GSB_ERR_INVALID, "sort limited to 2^30 - 1 pairs");
+    CK(cudaSetDevice(ctx->device));
+    int rc = wait_frame(ctx);
+    if (rc != GSB_OK) return rc;
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    // private look-back storage sized for m (the frame path uses the arena's)
+    const uint32_t tiles = (uint32_t)((m + sort_tile_items() - 1) / sort_tile_items());
+    unsigned long long* status = nullptr;
+    CK(dev_alloc(&status, (size_t)tiles * 256));
+    cudaError_t e = cudaMemsetAsync(status, 0, (size_t)tiles * 256 * 8, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->ctl, 0, sizeof(Control), s);
+    const uint32_t m32 = (uint32_t)m;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->ctl->num_instances, &m32, 4, cudaMemcpyHostToDevice, s);
+    SortParams sp{};
+    sp.keys[0] = reinterpret_cast<unsigned long long*>(keys);
+    sp.keys[1] = reinterpret_cast<unsigned long long*>(keys_tmp);
+    sp.vals[0] = vals;
+    sp.vals[1] = vals_tmp;
+    sp.d_m = &ctx->ctl->num_instances;
+    sp.m_hint = m32;
+    sp.key_bits = key_bits;
+    sp.status = status;
+    sp.status_tiles = tiles;
+    sp.epoch_base = 8;
+    sp.ctl = ctx->ctl;
+    sp.num_sms = ctx->num_sms;
+    sp.events = nullptr;
+    uint32_t passes = 0;
+    if (e == cudaSuccess) e = launch_sort(sp, &passes, s);
+    if (e == cudaSuccess && (passes & 1)) {  // odd pass count: bring the result back to the "Even" buffers
+        e = cudaMemcpyAsync(keys, keys_tmp, m * 8, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(vals, vals_tmp, m * 4, cudaMemcpyDeviceToDevice, s);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // m32/status lifetime
+    cudaFree(status);
+    if (e != cudaSuccess) return fail(ctx, GSB_ERR_CUDA, "gsb_sort_pairs", e);
+    return GSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// gsb_blend.cu -- per-16x16-tile front-to-back alpha blending.
+// Replaces render.comp:30-99 (dispatch src/Renderer.cpp:654-677).  The reference makes every
+// pixel thread gather idx + uv + conic + colour from global memory for every Gaussian of the
+// tile's run (render.comp:62-65,87; README.md:87 lists staging as a TODO).  Here one CTA owns one
+// tile, stages the run in batches of 256 compact 48-B records into shared memory once, and all
+// 256 pixel threads then read each record as a shared-memory broadcast.  The per-pixel `break`
+// (render.comp:83-85) becomes a per-thread done flag + a block-wide vote per batch.
+//
+// EXACT mode: -fmad=false, ops in render.comp's order, exp = the fixed IEEE sequence below
+// (bit-identical to oracle exp-mode 1).  FAST mode: explicit FMA + ex2.approx.
+#include "gsb_internal.cuh"
+
+namespace gsb {
+
+namespace {
+
+constexpr int BLEND_THREADS = 256;
+
+// Bit-defined exp for x in [-87, 0]; mirrors gso_exp_shared() in oracle/gs_oracle.c op for op.
+__device__ __forceinline__ float exp_shared(float x) {
+    x = fmaxf(x, -87.0f);
+    const float t = __fmul_rn(x, 1.44269504088896341f);
+    const float n = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);  // rint(t)
+    float r = __fmaf_rn(n, -0.693359375f, x);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    const float z = __fmul_rn(r, r);
+    float y = __fmaf_rn(1.9875691500e-4f, r, 1.3981999507e-3f);
+    y = __fmaf_rn(y, r, 8.3334519073e-3f);
+    y = __fmaf_rn(y, r, 4.1665795894e-2f);
+    y = __fmaf_rn(y, r, 1.6666665459e-1f);
+    y = __fmaf_rn(y, r, 5.0000001201e-1f);
+    y = __fmaf_rn(y, z, r);
+    y = __fadd_rn(y, 1.0f);
+    const int ni = (int)n;
+    return __fmul_rn(y, __int_as_float((ni + 127) << 23));
+}
+
+__device__ __forceinline__ uint32_t unorm8(float v) {
+    v = fminf(fmaxf(v, 0.0f), 1.0f);  // NaN -> 0
+    return __float2uint_rn(v * 255.0f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__ BlendParams P) {
+    __shared__ float4 s_r0[BLEND_THREADS];  // uv.x uv.y conic.x conic.y
+    __shared__ float4 s_r1[BLEND_THREADS];  // conic.z opacity r g
+    __shared__ float s_b[BLEND_THREADS];    // b
+    __shared__ uint32_t s_used;
+
+    const int tid = threadIdx.x;
+    const uint32_t tx = blockIdx.x % P.tiles_x;
+    const uint32_t ty = P.tile_row_begin + blockIdx.x / P.tiles_x;
+    const uint2 range = P.ranges[ty * P.tiles_x + tx];  // render.comp:43-44
+    const uint32_t px = tx * GSB_TILE + (tid & 15), py = ty * GSB_TILE + (tid >> 4);
+    const bool inside = px < P.width && py < P.height;  // :37-39
+    const float fx = (float)px, fy = (float)py;
+    if (tid == 0) s_used = 0;
+    __syncthreads();
+
+    float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+    bool done = !inside;
+    uint32_t used = 0;
+
+    for (uint32_t base = range.x; base < range.y; base += BLEND_THREADS) {
+        const uint32_t cnt = min((uint32_t)BLEND_THREADS, range.y - base);
+        if ((uint32_t)tid < cnt) {
+            const uint32_t cid = __ldg(P.vals + base + tid);
+            const float4* rec = P.recs + (size_t)cid * 3;
+            s_r0[tid] = __ldg(rec);
+            s_r1[tid] = __ldg(rec + 1);
+            s_b[tid] = __ldg(reinterpret_cast<const float*>(rec + 2));
+        }
+        __syncthreads();
+        if (!done) {
+            uint32_t j = 0;
+            for (; j < cnt; j++) {
+                const float4 a = s_r0[j];
+                const float4 b = s_r1[j];
+                const float dx = a.x - fx, dy = a.y - fy;  // :64
+                float alpha;
+                if (MODE == GSB_MODE_EXACT) {
+                    const float power = -0.5f * ((a.z * dx) * dx + (b.x * dy) * dy) - (a.w * dx) * dy;  // :66
+                    if (power > 0.0f) continue;   // :68-70
+                    if (power < -5.55f) continue;  // alpha <= exp(-5.55) < 1/255 because opacity <= 1
+                    alpha = fminf(0.99f, b.y * exp_shared(power));  // :77
+                } else {
+                    const float q = fmaf(a.z * dx, dx, (b.x * dy) * dy);
+                    const float power = fmaf(-0.5f, q, -(a.w * dx) * dy);
+                    if (power > 0.0f) continue;
+                    if (power < -5.55f) continue;
+                    alpha = fminf(0.99f, b.y * __expf(power));
+                }
+                if (alpha < 1.0f / 255.0f) continue;  // :78-80
+                const float test_T = T * (1.0f - alpha);  // :82
+                if (test_T < 0.0001f) {                   // :83-85
+                    done = true;
+                    used = base - range.x + j + 1;
+                    break;
+                }
+                if (MODE == GSB_MODE_EXACT) {
+                    c0 = c0 + (b.z * alpha) * T;  // :87
+                    c1 = c1 + (b.w * alpha) * T;
+                    c2 = c2 + (s_b[j] * alpha) * T;
+                } else {
+                    const float w = alpha * T;
+                    c0 = fmaf(b.z, w, c0);
+                    c1 = fmaf(b.w, w, c1);
+                    c2 = fmaf(s_b[j], w, c2);
+                }
+                T = test_T;  // :88
+            }
+            if (!done) used = base - range.x + cnt;
+        }
+        if (__syncthreads_and(done)) break;
+    }
+
+    if (inside) {
+        atomicMax(&s_used, used);
+        const uint32_t row = py - P.tile_row_begin * GSB_TILE;
+        unsigned char* dst = static_cast<unsigned char*>(P.out) + (size_t)row * P.row_pitch_bytes;
+        if (P.format == GSB_FORMAT_RGBA32F) {
+            reinterpret_cast<float4*>(dst)[px] = make_float4(c0, c1, c2, 1.0f);  // :98 vec4(c, 1)
+        } else {
+            const uint32_t r = unorm8(c0), g = unorm8(c1), b = unorm8(c2);
+            const uint32_t v = (P.format == GSB_FORMAT_BGRA8) ? (b | (g << 8) | (r << 16) | 0xff000000u)
+                                                              : (r | (g << 8) | (b << 16) | 0xff000000u);
+            reinterpret_cast<uint32_t*>(dst)[px] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_used) atomicAdd(&P.ctl->blend_consumed, (unsigned long long)s_used);
+}
+
+}  // namespace
+
+cudaError_t launch_blend(const BlendParams& p, cudaStream_t s) {
+    const uint32_t rows = p.tile_row_end - p.tile_row_begin;
+    const uint32_t blocks = rows * p.tiles_x;
+    if (blocks == 0) return cudaSuccess;
+    if (p.mode == GSB_MODE_EXACT) k_blend<GSB_MODE_EXACT><<<blocks, BLEND_THREADS, 0, s>>>(p);
+    else k_blend<GSB_MODE_FAST><<<blocks, BLEND_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gsb

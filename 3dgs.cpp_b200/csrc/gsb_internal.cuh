@@ -1,0 +1,99 @@
+// gsb_internal.cuh -- shared declarations of libgsb200 (not part of the public ABI).
+//
+// Device data layout (HBM), all fp32:
+//   scene   pos_op[N]  float4 (x, y, z, opacity)            16 B  coalesced LDG.128
+//           cov_a[N]   float4 (S00, S01, S02, S11)          16 B
+//           cov_b[N]   float2 (S12, S22)                     8 B
+//           sh[N][48]  RGB-interleaved degree-3 SH         192 B  read by cull survivors only
+//   frame   recs[Nv][3] float4  compacted per-survivor blend record (48 B):
+//               r0 = (uv.x, uv.y, conic.x, conic.y)
+//               r1 = (conic.z, opacity, color.r, color.g)
+//               r2 = (color.b, depth, radius, bits(original index))
+//           keys[2][cap] u64 = (tile << 32 | bits(depth)), vals[2][cap] u32 = compact id
+//           ranges[T] uint2 (start, end) per tile
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "gs_b200.h"
+
+#define GSB_TILE 16
+
+namespace gsb {
+
+// ---- per-frame control block (device memory, zeroed by one memset at frame start) ----
+struct Control {
+    uint32_t pre_ticket;       // chunk tickets of k_preprocess
+    uint32_t sort_ticket[8];   // tile tickets, one per radix pass
+    uint32_t ranges_ticket;
+    uint32_t num_visible;      // N_v
+    uint32_t num_instances;    // M clamped to the arena capacity
+    uint32_t overflow;         // 1 if M_total > capacity
+    uint32_t pad0;
+    unsigned long long instances_total;  // unclamped M
+    unsigned long long blend_consumed;
+    uint32_t hist[8][256];     // global digit histograms of the Onesweep sort
+};
+
+struct PreprocessParams {
+    const float4* pos_op;
+    const float4* cov_a;
+    const float2* cov_b;
+    const float* sh;
+    uint32_t n;
+    gsb_uniforms ubo;
+    uint32_t tile_row_begin, tile_row_end;  // band clip (multi-GPU); [0, tiles_y) = whole frame
+    // outputs
+    float4* recs;
+    unsigned long long* keys;
+    uint32_t* vals;
+    uint32_t capacity;
+    unsigned long long* status;  // decoupled look-back words, one per 256-Gaussian chunk
+    Control* ctl;
+    // debug outputs (may be null)
+    uint32_t* dbg_tiles;  // N
+    uint32_t* dbg_scan;   // N inclusive
+    uint4* dbg_aabb;      // N
+};
+
+cudaError_t launch_cov3d(const float* vtx_aos, uint64_t count, uint64_t dst_offset, float4* pos_op,
+                         float4* cov_a, float2* cov_b, float* sh, float scale_factor, cudaStream_t s);
+cudaError_t launch_preprocess(const PreprocessParams& p, bool debug, cudaStream_t s);
+
+struct SortParams {
+    unsigned long long* keys[2];
+    uint32_t* vals[2];
+    const uint32_t* d_m;       // device pointer to M
+    uint32_t m_hint;           // host estimate of M (sizes the grids only; any value is correct)
+    uint32_t key_bits;
+    unsigned long long* status;  // epoch-tagged look-back words [tiles][256]
+    uint32_t status_tiles;     // capacity of status in tiles
+    uint32_t epoch_base;       // unique per sort call; pass p uses epoch_base + p
+    Control* ctl;              // uses ctl->hist and ctl->sort_ticket (must be zero on entry)
+    int num_sms;
+    cudaEvent_t* events;       // optional: events[0] after the histogram, events[1 + p] after pass p
+};
+// Returns the number of passes P via *passes; sorted data ends in keys[P & 1].
+cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s);
+uint32_t sort_tile_items();
+
+cudaError_t launch_tile_ranges(const unsigned long long* keys, const uint32_t* d_m, uint32_t m_hint,
+                               uint2* ranges, uint32_t num_tiles, int num_sms, cudaStream_t s);
+
+struct BlendParams {
+    const float4* recs;
+    const uint32_t* vals;
+    const uint2* ranges;
+    uint32_t width, height, tiles_x;
+    uint32_t tile_row_begin, tile_row_end;
+    void* out;              // first pixel row of the band
+    size_t row_pitch_bytes;
+    int format;             // gsb_format
+    int mode;               // gsb_mode
+    Control* ctl;
+};
+cudaError_t launch_blend(const BlendParams& p, cudaStream_t s);
+
+}  // namespace gsb

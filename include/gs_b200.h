@@ -1,0 +1,173 @@
+/*
+ * gs_b200.h -- C ABI of libgsb200.so: the B200 (sm_100a) CUDA replacement for the per-frame
+ * compute path of shg8/3DGS.cpp (project+SH -> bin -> sort -> blend).
+ *
+ * The reference has no plugin/FFI seam for this path; the seam is compile-time inside
+ * Renderer/GSScene.  Every entry point below therefore names the reference
+ * code it replaces (paths relative to /root/reference).  A maintainer swaps the Vulkan
+ * dispatch for these calls as shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns
+ * GSB_OK (0) or a negative gsb_status and never throws; gsb_last_error() gives the text.
+ * A context is single-owner: one CUDA device, calls from one thread at a time (the reference
+ * is single-threaded with FRAMES_IN_FLIGHT = 1, src/vulkan/VulkanContext.h:6).
+ * There is NO CPU fallback: without a CUDA device gsb_create() fails with GSB_ERR_NO_DEVICE.
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1
+
+typedef struct gsb_ctx gsb_ctx;
+
+typedef enum gsb_status {
+    GSB_OK = 0,
+    GSB_ERR_INVALID = -1,   /* bad argument */
+    GSB_ERR_NO_DEVICE = -2, /* no usable CUDA device (the product has no CPU path) */
+    GSB_ERR_CUDA = -3,      /* CUDA runtime error, see gsb_last_error */
+    GSB_ERR_NO_SCENE = -4,  /* render before gsb_scene_upload */
+    GSB_ERR_OOM = -5,       /* device allocation failed */
+    GSB_ERR_OVERFLOW = -6   /* instance arena could not be grown enough */
+} gsb_status;
+
+/* Renderer::UniformBuffer -- src/Renderer.h:21-29 == preprocess.comp:16-24 (std140, 160 bytes,
+ * column-major mat4).  Produced on the host by Renderer::updateUniforms (src/Renderer.cpp:719-754). */
+typedef struct gsb_uniforms {
+    float camera_position[4];
+    float proj_mat[16];
+    float view_mat[16];
+    uint32_t width;
+    uint32_t height;
+    float tan_fovx;
+    float tan_fovy;
+} gsb_uniforms;
+
+/* VertexAttribute -- src/shaders/common.glsl:42-49 == Renderer.h:31-38; only used by
+ * gsb_debug_download(GSB_BUF_ATTR) so intermediates can be diffed against the reference layout. */
+typedef struct gsb_vertex_attribute {
+    float conic_opacity[4];
+    float color_radii[4];
+    uint32_t aabb[4];
+    float uv[2];
+    float depth;
+    uint32_t magic;
+} gsb_vertex_attribute;
+
+/* Output image formats.  The reference stores vec4(c,1) into a B8G8R8A8_UNORM swapchain image
+ * (render.comp:98, src/vulkan/Swapchain.cpp:24); RGBA32F is the un-quantised value of that store. */
+typedef enum gsb_format {
+    GSB_FORMAT_RGBA32F = 0, /* float4 per pixel, 16 B */
+    GSB_FORMAT_RGBA8 = 1,   /* UNORM8, R,G,B,A byte order */
+    GSB_FORMAT_BGRA8 = 2    /* UNORM8, B,G,R,A byte order (the reference swapchain format) */
+} gsb_format;
+
+/* Arithmetic mode of the blend stage.
+ * EXACT: every fp32 op is a single IEEE operation in render.comp's order and exp() is the fixed
+ *        operation sequence documented in DESIGN.md; bit-identical to oracle exp-mode 1.
+ * FAST : FMA contraction + ex2.approx; same algorithm, results within ~1e-6 of EXACT except at
+ *        the shader's own step functions. */
+typedef enum gsb_mode { GSB_MODE_EXACT = 0, GSB_MODE_FAST = 1 } gsb_mode;
+
+typedef enum gsb_memory { GSB_MEM_HOST = 0, GSB_MEM_DEVICE = 1 } gsb_memory;
+
+/* Buffers retrievable with gsb_debug_download, in the REFERENCE's layouts. */
+typedef enum gsb_buffer {
+    GSB_BUF_COV3D = 0,         /* scene->cov3DBuffer: N * 6 float                 (GSScene.cpp:158) */
+    GSB_BUF_ATTR = 1,          /* vertexAttributeBuffer: N * gsb_vertex_attribute (Renderer.cpp:169); culled entries zero */
+    GSB_BUF_TILES_OVERLAP = 2, /* tileOverlapBuffer: N * u32                      (Renderer.cpp:170) */
+    GSB_BUF_PREFIX_SUM = 3,    /* inclusive scan: N * u32                         (Renderer.cpp:215) */
+    GSB_BUF_KEYS_UNSORTED = 4, /* sortKBufferEven after preprocess_sort: M * u64  (Renderer.cpp:235) */
+    GSB_BUF_VALS_UNSORTED = 5, /* sortVBufferEven after preprocess_sort: M * u32  (Renderer.cpp:239) */
+    GSB_BUF_KEYS_SORTED = 6,   /* sortKBufferEven after the 8 passes: M * u64 */
+    GSB_BUF_VALS_SORTED = 7,   /* sortVBufferEven after the 8 passes: M * u32 (Gaussian indices) */
+    GSB_BUF_TILE_BOUNDARY = 8  /* tileBoundaryBuffer: T * 2 u32                   (Renderer.cpp:321) */
+} gsb_buffer;
+
+/* The reference's six timestamp pairs (src/Renderer.cpp:484-699) + its "instances" text metric
+ * (:540).  preprocess/prefix_sum/preprocess_sort are ONE fused kernel here: its time is reported
+ * under preprocess_ms and the other two are 0. */
+typedef struct gsb_stats {
+    uint64_t num_gaussians;     /* N */
+    uint64_t num_visible;       /* N_v: survivors of the three culls */
+    uint64_t num_instances;     /* M  ("instances", Renderer.cpp:540) */
+    uint64_t blend_consumed;    /* sum over tiles of run entries read before the tile terminated */
+    uint64_t instance_capacity; /* current arena capacity in instances */
+    uint32_t sort_passes;       /* P radix passes used for this frame */
+    uint32_t regrow_count;      /* times the arena was regrown and the frame re-rendered so far */
+    float preprocess_ms, prefix_sum_ms, preprocess_sort_ms, sort_ms, tile_boundary_ms, render_ms;
+    float frame_ms;         /* first kernel to last kernel of the frame */
+    float sort_hist_ms;     /* the one histogram kernel inside sort_ms */
+    float sort_pass_ms[8];  /* each Onesweep pass kernel inside sort_ms (first sort_passes entries) */
+} gsb_stats;
+
+/* ---- lifetime: replaces Renderer::initializeVulkan + create*Pipeline (Renderer.cpp:119-155,166-364) ---- */
+int gsb_abi_version(void);
+int gsb_device_count(void);
+int gsb_create(int device, gsb_ctx **out);
+void gsb_destroy(gsb_ctx *ctx);
+/* Text of the last error on ctx (ctx == NULL: last gsb_create error on this thread). */
+const char *gsb_last_error(const gsb_ctx *ctx);
+
+/* ---- scene: replaces vertexBuffer->uploadFrom + GSScene::precomputeCov3D (GSScene.cpp:61,157-184) ----
+ * vertices: n records of GSScene::Vertex (src/GSScene.h:41-46): 60 floats =
+ * position(xyz,1) scale_opacity(exp(s),sigmoid(o)) rotation(w,x,y,z normalised) sh[48] (RGB-interleaved),
+ * i.e. exactly what GSScene::load (GSScene.cpp:36-59) stages.  mem says where `vertices` lives.
+ * Precomputes cov3D on the device (precomp_cov3d.comp:25-48, scale_factor 1.0 as GSScene.cpp:176). */
+int gsb_scene_upload(gsb_ctx *ctx, const float *vertices, uint64_t n, gsb_memory mem);
+uint64_t gsb_scene_size(const gsb_ctx *ctx);
+
+/* ---- configuration ---- */
+int gsb_set_mode(gsb_ctx *ctx, gsb_mode mode);
+/* debug != 0: keep every intermediate so gsb_debug_download works (extra HBM traffic). */
+int gsb_set_debug(gsb_ctx *ctx, int debug);
+/* per-stage cudaEvent timers (the QueryManager analogue, Renderer.cpp:85-100). Default on. */
+int gsb_set_timers(gsb_ctx *ctx, int enabled);
+/* Pre-size the (tile,depth) instance arena (the reference's sortBufferSizeMultiplier,
+ * Renderer.cpp:541-563, grows N*k on overflow; this does the same between frames). */
+int gsb_reserve_instances(gsb_ctx *ctx, uint64_t capacity);
+
+/* ---- the frame: replaces Renderer::draw()'s two submits (Renderer.cpp:388-405), i.e.
+ * preprocess.comp -> prefix_sum.comp x(log2N+1) -> preprocess_sort.comp -> 8x(hist.comp, sort.comp)
+ * -> tile_boundary.comp -> render.comp, without the mid-frame fence + host read of M (:391,:538).
+ *
+ * Renders tile rows [tile_row_begin, tile_row_end) of the (ubo->width x ubo->height) frame
+ * (pass 0, UINT32_MAX for the whole frame; a sub-range is the multi-GPU band of SURVEY 8e).
+ * `out` receives pixel rows [16*tile_row_begin, min(H, 16*tile_row_end)) densely, row-major,
+ * `row_pitch_bytes` apart (0 = tight).  out_mem says whether `out` is host or device memory.
+ * `stream` is a cudaStream_t (NULL = the context's own stream).  The call returns when the frame
+ * (and, for host output, the copy) has completed.  If the instance arena overflows, the arena is
+ * regrown and the frame re-rendered transparently (the reference's retry, Renderer.cpp:397-399). */
+int gsb_render(gsb_ctx *ctx, const gsb_uniforms *ubo, uint32_t tile_row_begin, uint32_t tile_row_end,
+               void *out, size_t row_pitch_bytes, gsb_memory out_mem, gsb_format fmt, void *stream);
+
+/* Enqueue-only variant for pipelined callers (bench e2e): never synchronises, never regrows;
+ * overflow is reported by the next gsb_get_stats()/gsb_render().  out must be device memory. */
+int gsb_render_async(gsb_ctx *ctx, const gsb_uniforms *ubo, uint32_t tile_row_begin,
+                     uint32_t tile_row_end, void *out_device, size_t row_pitch_bytes, gsb_format fmt,
+                     void *stream);
+
+/* Waits for the last frame and fills stats (the retrieveTimestamps analogue, Renderer.cpp:85-100). */
+int gsb_get_stats(gsb_ctx *ctx, gsb_stats *out);
+
+/* Size in bytes of a debug buffer for the last frame (0 if unavailable), and its download. */
+size_t gsb_debug_size(gsb_ctx *ctx, gsb_buffer which);
+int gsb_debug_download(gsb_ctx *ctx, gsb_buffer which, void *dst, size_t bytes);
+
+/* ---- standalone stage entry points (device pointers), used by tests/bench to pin each kernel ---- */
+/* Onesweep LSD radix sort of (u64 key, u32 value) pairs over the low `key_bits` bits; stable.
+ * Replaces the 8x(hist.comp + sort.comp) loop (Renderer.cpp:598-629).  Sorted data ends in
+ * keys/vals (the "Even" buffers, Renderer.cpp:641); keys_tmp/vals_tmp are the "Odd" buffers. */
+int gsb_sort_pairs(gsb_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                   uint64_t m, uint32_t key_bits, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */

@@ -1,0 +1,742 @@
+/*
+ * gs_oracle.c -- CPU oracle for the 3DGS.cpp per-frame compute path (see gs_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY -- never linked into or called from the product path.
+ * PARITY UNPINNED -- the reference has no tests/golden vectors for this path; this is a
+ * restatement by formula of the cited lines of /root/reference (shg8/3DGS.cpp @ f614d66).
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math [-fopenmp] (oracle/Makefile).
+ * fp32 throughout; every +,-,*,/ and sqrt is a single correctly-rounded IEEE operation
+ * evaluated in the order the GLSL source spells (left to right), so that a CUDA kernel
+ * built with explicit __f*_rn intrinsics can be compared bit for bit.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "gs_oracle.h"
+
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define TILE_W 16 /* common.glsl:1 */
+#define TILE_H 16 /* common.glsl:2 */
+
+static int g_exp_mode = 0;
+void gso_set_exp_mode(int mode) { g_exp_mode = mode; }
+int gso_get_exp_mode(void) { return g_exp_mode; }
+void gso_free(void *p) { free(p); }
+
+int gso_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * "Shared-definition" exp for x in [-87, 0] (the blend only evaluates power <= 0).
+ * Cody-Waite range reduction, Cephes-style degree-5 polynomial, every step one IEEE op.
+ * ---------------------------------------------------------------------------------------- */
+float gso_exp_shared(float x) {
+    if (x < -87.0f) x = -87.0f;
+    const float t = x * 1.44269504088896341f;
+    const float magic = 12582912.0f; /* 1.5 * 2^23: (t + magic) - magic == rint(t) for |t| < 2^22 */
+    volatile float tm = t + magic;   /* volatile: forbid algebraic folding */
+    const float n = tm - magic;
+    float r = fmaf(n, -0.693359375f, x);
+    r = fmaf(n, 2.12194440e-4f, r);
+    const float z = r * r;
+    float y = fmaf(1.9875691500e-4f, r, 1.3981999507e-3f);
+    y = fmaf(y, r, 8.3334519073e-3f);
+    y = fmaf(y, r, 4.1665795894e-2f);
+    y = fmaf(y, r, 1.6666665459e-1f);
+    y = fmaf(y, r, 5.0000001201e-1f);
+    y = fmaf(y, z, r);
+    y = y + 1.0f;
+    const int ni = (int)n; /* exact: n is integral, -126 <= n <= 0 */
+    union {
+        uint32_t u;
+        float f;
+    } s;
+    s.u = (uint32_t)(ni + 127) << 23;
+    return y * s.f; /* exact scaling (no underflow for n >= -126) */
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Small column-major matrix helpers (GLSL / glm semantics, m[c*R + r]).
+ * ---------------------------------------------------------------------------------------- */
+static void mat3_mul(const float *a, const float *b, float *o) { /* o = a * b */
+    float t[9];
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) {
+            float s = a[0 * 3 + r] * b[c * 3 + 0];
+            s = s + a[1 * 3 + r] * b[c * 3 + 1];
+            s = s + a[2 * 3 + r] * b[c * 3 + 2];
+            t[c * 3 + r] = s;
+        }
+    memcpy(o, t, sizeof t);
+}
+static void mat3_transpose(const float *a, float *o) {
+    float t[9];
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) t[c * 3 + r] = a[r * 3 + c];
+    memcpy(o, t, sizeof t);
+}
+static void mat4_mul(const float *a, const float *b, float *o) { /* glm mat4 operator* */
+    float t[16];
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) {
+            float s = a[0 * 4 + r] * b[c * 4 + 0];
+            s = s + a[1 * 4 + r] * b[c * 4 + 1];
+            s = s + a[2 * 4 + r] * b[c * 4 + 2];
+            s = s + a[3 * 4 + r] * b[c * 4 + 3];
+            t[c * 4 + r] = s;
+        }
+    memcpy(o, t, sizeof t);
+}
+static void mat4_mul_vec4(const float *m, const float *v, float *o) { /* GLSL mat4 * vec4 */
+    for (int r = 0; r < 4; r++) {
+        float s = m[0 * 4 + r] * v[0];
+        s = s + m[1 * 4 + r] * v[1];
+        s = s + m[2 * 4 + r] * v[2];
+        s = s + m[3 * 4 + r] * v[3];
+        o[r] = s;
+    }
+}
+
+/* glm::inverse(mat4) -- glm 1.0.0 detail/func_matrix.inl compute_inverse<4,4> (cofactor form).
+ * glm is a FetchContent dependency (CMakeLists.txt:31-36), not vendored: restated from its
+ * published algorithm. Call site: src/Renderer.cpp:728. */
+static void mat4_inverse(const float *m, float *o) {
+#define M(c, r) m[(c) * 4 + (r)]
+    float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3);
+    float c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+    float c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+    float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+    float c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3);
+    float c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+    float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2);
+    float c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+    float c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+    float c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+    float c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3);
+    float c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+    float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2);
+    float c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+    float c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+    float c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+    float c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1);
+    float c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+    float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    float v0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)};
+    float v1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+    float v2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)};
+    float v3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+    const float sa[4] = {+1.f, -1.f, +1.f, -1.f}, sb[4] = {-1.f, +1.f, -1.f, +1.f};
+    float inv[16];
+    for (int i = 0; i < 4; i++) {
+        float i0 = (v1[i] * f0[i] - v2[i] * f1[i]) + v3[i] * f2[i];
+        float i1 = (v0[i] * f0[i] - v2[i] * f3[i]) + v3[i] * f4[i];
+        float i2 = (v0[i] * f1[i] - v1[i] * f3[i]) + v3[i] * f5[i];
+        float i3 = (v0[i] * f2[i] - v1[i] * f4[i]) + v2[i] * f5[i];
+        inv[0 * 4 + i] = i0 * sa[i];
+        inv[1 * 4 + i] = i1 * sb[i];
+        inv[2 * 4 + i] = i2 * sa[i];
+        inv[3 * 4 + i] = i3 * sb[i];
+    }
+    float d0 = M(0, 0) * inv[0 * 4 + 0], d1 = M(0, 1) * inv[1 * 4 + 0];
+    float d2 = M(0, 2) * inv[2 * 4 + 0], d3 = M(0, 3) * inv[3 * 4 + 0];
+    float det = (d0 + d1) + (d2 + d3);
+    float ood = 1.0f / det;
+    for (int i = 0; i < 16; i++) o[i] = inv[i] * ood;
+#undef M
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A0. GSScene::load, src/GSScene.cpp:36-59
+ * ---------------------------------------------------------------------------------------- */
+void gso_load_records(const float *rec, uint64_t n, float *vtx) {
+    for (uint64_t i = 0; i < n; i++) {
+        const float *s = rec + i * GSO_RECORD_FLOATS; /* pos3 normal3 shs48 opacity scale3 rot4 */
+        float *v = vtx + i * GSO_VERTEX_FLOATS;
+        const float *shs = s + 6, *scale = s + 55, *rot = s + 58;
+        const float opacity = s[54];
+        v[0] = s[0];
+        v[1] = s[1];
+        v[2] = s[2];
+        v[3] = 1.0f; /* :41 */
+        v[4] = expf(scale[0]);
+        v[5] = expf(scale[1]);
+        v[6] = expf(scale[2]);
+        v[7] = 1.0f / (1.0f + expf(-opacity)); /* :44 (std::exp(float)) */
+        /* :45 glm::normalize(vec4) = v * inversesqrt(dot(v,v)); glm inversesqrt = 1/sqrt(x);
+         * glm dot(vec4) = (tmp.x + tmp.y) + (tmp.z + tmp.w) with tmp = a*b. */
+        float t0 = rot[0] * rot[0], t1 = rot[1] * rot[1], t2 = rot[2] * rot[2], t3 = rot[3] * rot[3];
+        float d = (t0 + t1) + (t2 + t3);
+        float inv = 1.0f / sqrtf(d);
+        v[8] = rot[0] * inv;
+        v[9] = rot[1] * inv;
+        v[10] = rot[2] * inv;
+        v[11] = rot[3] * inv;
+        float *o = v + 12;
+        o[0] = shs[0];
+        o[1] = shs[1];
+        o[2] = shs[2]; /* :47-49 */
+        const int SH_N = 16;
+        for (int j = 1; j < SH_N; j++) { /* :51-55 */
+            o[j * 3 + 0] = shs[(j - 1) + 3];
+            o[j * 3 + 1] = shs[(j - 1) + SH_N + 2];
+            o[j * 3 + 2] = shs[(j - 1) + SH_N * 2 + 1];
+        }
+    }
+}
+
+/* src/GSScene.cpp:99-149 (header: only "element vertex <N>" matters) + :26-68 */
+float *gso_load_ply(const char *path, uint64_t *n_out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return NULL;
+    char line[1024];
+    long long nverts = -1;
+    int header_end = 0;
+    while (fgets(line, sizeof line, f)) {
+        char tok[64] = {0}, tok2[64] = {0};
+        long long cnt = 0;
+        int k = sscanf(line, "%63s %63s %lld", tok, tok2, &cnt);
+        if (k >= 3 && strcmp(tok, "element") == 0 && strcmp(tok2, "vertex") == 0) nverts = cnt;
+        if (k >= 1 && strcmp(tok, "end_header") == 0) {
+            header_end = 1;
+            break;
+        }
+    }
+    if (!header_end || nverts < 0) {
+        fclose(f);
+        return NULL;
+    }
+    uint64_t n = (uint64_t)nverts;
+    float *rec = (float *)malloc((size_t)n * GSO_RECORD_FLOATS * sizeof(float));
+    float *vtx = (float *)malloc((size_t)n * GSO_VERTEX_FLOATS * sizeof(float));
+    if ((n && (!rec || !vtx)) || fread(rec, sizeof(float) * GSO_RECORD_FLOATS, n, f) != n) {
+        free(rec);
+        free(vtx);
+        fclose(f);
+        return NULL;
+    }
+    fclose(f);
+    gso_load_records(rec, n, vtx);
+    free(rec);
+    *n_out = n;
+    return vtx;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A1. precomp_cov3d.comp:25-48 + rotationFromQuaternion, common.glsl:51-75
+ * ---------------------------------------------------------------------------------------- */
+static void rotation_from_quaternion(const float *q, float *R) { /* q = vertex.rotation */
+    float qx = q[1], qy = q[2], qz = q[3], qw = q[0]; /* common.glsl:52-55 */
+    float qx2 = qx * qx, qy2 = qy * qy, qz2 = qz * qz;
+    /* rotationMatrix[c][r], common.glsl:62-72 */
+    R[0 * 3 + 0] = (1.0f - 2.0f * qy2) - 2.0f * qz2;
+    R[0 * 3 + 1] = (2.0f * qx) * qy - (2.0f * qz) * qw;
+    R[0 * 3 + 2] = (2.0f * qx) * qz + (2.0f * qy) * qw;
+    R[1 * 3 + 0] = (2.0f * qx) * qy + (2.0f * qz) * qw;
+    R[1 * 3 + 1] = (1.0f - 2.0f * qx2) - 2.0f * qz2;
+    R[1 * 3 + 2] = (2.0f * qy) * qz - (2.0f * qx) * qw;
+    R[2 * 3 + 0] = (2.0f * qx) * qz - (2.0f * qy) * qw;
+    R[2 * 3 + 1] = (2.0f * qy) * qz + (2.0f * qx) * qw;
+    R[2 * 3 + 2] = (1.0f - 2.0f * qx2) - 2.0f * qy2;
+}
+
+void gso_cov3d(const float *vtx, uint64_t n, float scale_factor, float *cov) {
+    for (uint64_t i = 0; i < n; i++) {
+        const float *v = vtx + i * GSO_VERTEX_FLOATS;
+        float S[9] = {0}, R[9], Mm[9], Mt[9], C[9];
+        S[0] = v[4] * scale_factor; /* :31-34 */
+        S[4] = v[5] * scale_factor;
+        S[8] = v[6] * scale_factor;
+        rotation_from_quaternion(v + 8, R); /* :37 */
+        mat3_mul(S, R, Mm);                 /* :39 M = S * R */
+        mat3_transpose(Mm, Mt);
+        mat3_mul(Mt, Mm, C); /* :40 */
+        float *o = cov + i * 6;
+        o[0] = C[0 * 3 + 0]; /* :42-47 cov3d[c][r] */
+        o[1] = C[0 * 3 + 1];
+        o[2] = C[0 * 3 + 2];
+        o[3] = C[1 * 3 + 1];
+        o[4] = C[1 * 3 + 2];
+        o[5] = C[2 * 3 + 2];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A2. Renderer::updateUniforms, src/Renderer.cpp:719-754 (glm 1.0.0 semantics restated)
+ * ---------------------------------------------------------------------------------------- */
+void gso_uniforms_from_camera(const float pos[3], const float q[4], float fov_deg, float near_plane,
+                              float far_plane, uint32_t width, uint32_t height, gso_uniforms *out) {
+    memset(out, 0, sizeof *out);
+    out->width = width;
+    out->height = height;
+    out->camera_position[0] = pos[0];
+    out->camera_position[1] = pos[1];
+    out->camera_position[2] = pos[2];
+    out->camera_position[3] = 1.0f; /* :724 */
+
+    /* glm::mat4_cast(quat) -- gtc/quaternion.inl mat3_cast; q = (w,x,y,z) */
+    float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    float qxx = qx * qx, qyy = qy * qy, qzz = qz * qz, qxz = qx * qz, qxy = qx * qy, qyz = qy * qz;
+    float qwx = qw * qx, qwy = qw * qy, qwz = qw * qz;
+    float rot[16] = {0};
+    rot[0 * 4 + 0] = 1.0f - 2.0f * (qyy + qzz);
+    rot[0 * 4 + 1] = 2.0f * (qxy + qwz);
+    rot[0 * 4 + 2] = 2.0f * (qxz - qwy);
+    rot[1 * 4 + 0] = 2.0f * (qxy - qwz);
+    rot[1 * 4 + 1] = 1.0f - 2.0f * (qxx + qzz);
+    rot[1 * 4 + 2] = 2.0f * (qyz + qwx);
+    rot[2 * 4 + 0] = 2.0f * (qxz + qwy);
+    rot[2 * 4 + 1] = 2.0f * (qyz - qwx);
+    rot[2 * 4 + 2] = 1.0f - 2.0f * (qxx + qyy);
+    rot[3 * 4 + 3] = 1.0f;
+    /* glm::translate(mat4(1), v): Result[3] = m[0]*v0 + m[1]*v1 + m[2]*v2 + m[3] */
+    float tr[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int r = 0; r < 4; r++) {
+        float s = tr[0 * 4 + r] * pos[0];
+        s = s + tr[1 * 4 + r] * pos[1];
+        s = s + tr[2 * 4 + r] * pos[2];
+        tr[3 * 4 + r] = s + tr[3 * 4 + r];
+    }
+    float tr_rot[16], view[16];
+    mat4_mul(tr, rot, tr_rot);
+    mat4_inverse(tr_rot, view); /* :728 */
+
+    /* :730 float tan_fovx = std::tan(glm::radians(camera.fov) / 2.0)  (double division and tan) */
+    float radians = fov_deg * 0.01745329251994329576923690768489f;
+    float tan_fovx = (float)tan((double)radians / 2.0);
+    float tan_fovy = tan_fovx * (float)height / (float)width; /* :731 */
+
+    /* :733-736 glm::perspective == perspectiveRH_NO (no GLM_FORCE_* defines in the reference) */
+    float fovy = atanf(tan_fovy) * 2.0f;
+    float aspect = (float)width / (float)height;
+    float tan_half = tanf(fovy / 2.0f);
+    float persp[16] = {0};
+    persp[0 * 4 + 0] = 1.0f / (aspect * tan_half);
+    persp[1 * 4 + 1] = 1.0f / tan_half;
+    persp[2 * 4 + 2] = -(far_plane + near_plane) / (far_plane - near_plane);
+    persp[2 * 4 + 3] = -1.0f;
+    persp[3 * 4 + 2] = -(2.0f * far_plane * near_plane) / (far_plane - near_plane);
+    float proj[16];
+    mat4_mul(persp, view, proj);
+
+    for (int c = 0; c < 4; c++) { /* :738-750 */
+        view[c * 4 + 1] *= -1.0f;
+        view[c * 4 + 2] *= -1.0f;
+        proj[c * 4 + 1] *= -1.0f;
+    }
+    memcpy(out->view_mat, view, sizeof view);
+    memcpy(out->proj_mat, proj, sizeof proj);
+    out->tan_fovx = tan_fovx;
+    out->tan_fovy = tan_fovy;
+}
+
+/* Camera::translate: position += rotation * translation (glm operator*(quat, vec3)):
+ *   uv = cross(qv, v); uuv = cross(qv, uv); return v + ((uv * q.w) + uuv) * 2 */
+void gso_camera_translate(float pos[3], const float q[4], const float t[3]) {
+    float qv[3] = {q[1], q[2], q[3]};
+    float uv[3] = {qv[1] * t[2] - t[1] * qv[2], qv[2] * t[0] - t[2] * qv[0], qv[0] * t[1] - t[0] * qv[1]};
+    float uuv[3] = {qv[1] * uv[2] - uv[1] * qv[2], qv[2] * uv[0] - uv[2] * qv[0],
+                    qv[0] * uv[1] - uv[0] * qv[1]};
+    for (int i = 0; i < 3; i++) pos[i] = pos[i] + (t[i] + ((uv[i] * q[0]) + uuv[i]) * 2.0f);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A3. preprocess.comp
+ * ---------------------------------------------------------------------------------------- */
+static int f2i_trunc(float x) { /* GLSL int(float); saturating like cvt.rzi.s32.f32 where GLSL is undefined */
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT_MAX;
+    if (x <= -2147483648.0f) return INT_MIN;
+    return (int)x;
+}
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static const float SH_C0 = 0.28209479177387814f; /* common.glsl:16-33 */
+static const float SH_C1 = 0.4886025119029199f;
+static const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                               -1.0925484305920792f, 0.5462742152960396f};
+static const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                               0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                               -0.5900435899266435f};
+
+/* preprocess.comp:73-108 */
+static void compute_sh(const float *v, const float *cam, float *c) {
+    float d[3] = {v[0] - cam[0], v[1] - cam[1], v[2] - cam[2]};
+    float len = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]); /* length() */
+    float x = d[0] / len, y = d[1] / len, z = d[2] / len;         /* :77 */
+    const float *sh = v + 12;
+#define SH(k, ch) sh[(k) * 3 + (ch)]
+    float xx = x * x, yy = y * y;
+    float w6 = ((2.0f * z) * z - xx) - yy;
+    float w8 = xx - yy;
+    float w9 = (3.0f * x) * x - yy;
+    float w11 = ((4.0f * z) * z - xx) - yy;
+    float w12 = ((2.0f * z) * z - (3.0f * x) * x) - (3.0f * y) * y;
+    float w15 = xx - (3.0f * y) * y;
+    for (int ch = 0; ch < 3; ch++) {
+        float a = SH_C0 * SH(0, ch);
+        a = a - (SH_C1 * SH(1, ch)) * y;
+        a = a + (SH_C1 * SH(2, ch)) * z;
+        a = a - (SH_C1 * SH(3, ch)) * x;
+        a = a + ((SH_C2[0] * SH(4, ch)) * x) * y;
+        a = a + ((SH_C2[1] * SH(5, ch)) * y) * z;
+        a = a + (SH_C2[2] * SH(6, ch)) * w6;
+        a = a + ((SH_C2[3] * SH(7, ch)) * z) * x;
+        a = a + (SH_C2[4] * SH(8, ch)) * w8;
+        a = a + ((SH_C3[0] * SH(9, ch)) * w9) * y;
+        a = a + (((SH_C3[1] * SH(10, ch)) * x) * y) * z;
+        a = a + ((SH_C3[2] * SH(11, ch)) * w11) * y;
+        a = a + ((SH_C3[3] * SH(12, ch)) * z) * w12;
+        a = a + ((SH_C3[4] * SH(13, ch)) * x) * w11;
+        a = a + ((SH_C3[5] * SH(14, ch)) * w8) * z;
+        a = a + ((SH_C3[6] * SH(15, ch)) * x) * w15;
+        c[ch] = a + 0.5f; /* :100 */
+    }
+#undef SH
+    if (c[0] < 0.0f) c[0] = 0.0f; /* :102-104 -- only the red channel is clamped */
+}
+
+void gso_preprocess(const float *vtx, const float *cov, uint64_t n, const gso_uniforms *u,
+                    uint32_t tile_row_begin, uint32_t tile_row_end, gso_attr *attr, uint32_t *tiles) {
+    const int W = (int)u->width, H = (int)u->height;
+    const int tiles_x = (int)((u->width + TILE_W - 1) / TILE_W);  /* :125 */
+    const int tiles_y = (int)((u->height + TILE_H - 1) / TILE_H);
+    const float tan_fovx = u->tan_fovx, tan_fovy = u->tan_fovy;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t ii = 0; ii < (int64_t)n; ii++) {
+        const uint64_t i = (uint64_t)ii;
+        const float *v = vtx + i * GSO_VERTEX_FLOATS;
+        gso_attr *a = &attr[i];
+        memset(a, 0, sizeof *a); /* :127 color_radii.w = 0 */
+        tiles[i] = 0;            /* :128 */
+
+        float p_hom[4], p_view[4];
+        mat4_mul_vec4(u->proj_mat, v, p_hom); /* :130 */
+        float p_w = 1.0f / p_hom[3];          /* :131 */
+        float ndc[3] = {p_hom[0] * p_w, p_hom[1] * p_w, p_hom[2] * p_w};
+        mat4_mul_vec4(u->view_mat, v, p_view); /* :134 */
+        if (p_view[2] <= 0.2f) continue;       /* :135 */
+
+        /* get_projection_jacobian_approx, :34-50 */
+        float t[3] = {p_view[0], p_view[1], p_view[2]};
+        float limx = 1.3f * tan_fovx, limy = 1.3f * tan_fovy;
+        float txtz = t[0] / t[2], tytz = t[1] / t[2];
+        t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
+        t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
+        float focal_x = (float)u->width / (2.0f * tan_fovx);
+        float focal_y = (float)u->height / (2.0f * tan_fovy);
+        float J[9] = {focal_x / t[2], 0.0f, -(focal_x * t[0]) / (t[2] * t[2]), /* column 0 */
+                      0.0f, focal_y / t[2], -(focal_y * t[1]) / (t[2] * t[2]), /* column 1 */
+                      0.0f, 0.0f, 0.0f};
+        /* compute_cov2d, :52-66 */
+        float view3[9], Wm[9], Tm[9], Tt[9], tmp[9], c2[9];
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 3; r++) view3[c * 3 + r] = u->view_mat[c * 4 + r];
+        mat3_transpose(view3, Wm); /* :55 */
+        const float *cv = cov + i * 6;
+        float Sigma[9] = {cv[0], cv[1], cv[2], cv[1], cv[3], cv[4], cv[2], cv[4], cv[5]}; /* :56-60 */
+        mat3_mul(Wm, J, Tm);                                                              /* :61 */
+        mat3_transpose(Tm, Tt);
+        mat3_mul(Tt, Sigma, tmp);
+        mat3_mul(tmp, Tm, c2); /* :62 */
+        float m00 = c2[0 * 3 + 0] + 0.3f, m01 = c2[0 * 3 + 1], m10 = c2[1 * 3 + 0],
+              m11 = c2[1 * 3 + 1] + 0.3f; /* :63-65 */
+
+        float det = m00 * m11 - m10 * m01; /* determinant(mat2), :138 */
+        if (det <= 0.0f) continue;         /* :139-141 */
+        float ood = 1.0f / det;            /* inverse(mat2) as adj * (1/det), :142 */
+        float conic00 = m11 * ood, conic01 = -m01 * ood, conic11 = m00 * ood;
+
+        float mid = 0.5f * (m00 + m11); /* :146-151 */
+        float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+        float lambda1 = mid + sq, lambda2 = mid - sq;
+        float lambda = fmaxf(lambda1, lambda2);
+        float radii = ceilf(3.0f * sqrtf(lambda));
+
+        float uvx = ((ndc[0] + 1.0f) * (float)W - 1.0f) * 0.5f; /* ndc2Pix :110-113,:157 */
+        float uvy = ((ndc[1] + 1.0f) * (float)H - 1.0f) * 0.5f;
+
+        int bx0 = clampi(f2i_trunc((uvx - radii) / (float)TILE_W), 0, tiles_x); /* :159-164 */
+        int by0 = clampi(f2i_trunc((uvy - radii) / (float)TILE_H), 0, tiles_y);
+        /* "uv.x + radii + TILE_WIDTH - 1" is ((uv.x + radii) + 16) - 1 after macro substitution */
+        int bx1 = clampi(f2i_trunc((((uvx + radii) + (float)TILE_W) - 1.0f) / (float)TILE_W), 0, tiles_x);
+        int by1 = clampi(f2i_trunc((((uvy + radii) + (float)TILE_H) - 1.0f) / (float)TILE_H), 0, tiles_y);
+
+        /* multi-GPU band clip (not in the reference; identity for [0, UINT32_MAX)) */
+        if ((uint32_t)by0 < tile_row_begin) by0 = (int)tile_row_begin;
+        if ((uint32_t)by1 > tile_row_end) by1 = (int)tile_row_end;
+        if (by1 < by0) by1 = by0;
+
+        uint32_t nt = (uint32_t)(bx1 - bx0) * (uint32_t)(by1 - by0); /* :168 */
+        if (nt == 0) continue;                                       /* :169-171 */
+        a->conic_opacity[0] = conic00;
+        a->conic_opacity[1] = conic01;
+        a->conic_opacity[2] = conic11;
+        a->conic_opacity[3] = v[7]; /* :143-144 */
+        a->aabb[0] = (uint32_t)bx0;
+        a->aabb[1] = (uint32_t)by0;
+        a->aabb[2] = (uint32_t)bx1;
+        a->aabb[3] = (uint32_t)by1; /* :173 */
+        tiles[i] = nt;              /* :175 */
+        a->depth = p_view[2];       /* :176 */
+        a->color_radii[3] = radii;  /* :177 */
+        compute_sh(v, u->camera_position, a->color_radii); /* :178 */
+        a->uv[0] = uvx;
+        a->uv[1] = uvy;       /* :179 */
+        a->magic = GSO_MAGIC; /* :180 */
+    }
+}
+
+/* A4. prefix_sum.comp (Hillis-Steele, log2 N + 1 steps) computes exactly an inclusive scan. */
+uint64_t gso_scan_inclusive(const uint32_t *tiles, uint64_t n, uint32_t *scan) {
+    uint32_t s = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        s += tiles[i]; /* uint32 wraparound like the shader */
+        scan[i] = s;
+    }
+    return n ? scan[n - 1] : 0; /* Renderer.cpp:516-523,538: numInstances = scan[N-1] */
+}
+
+/* A5. preprocess_sort.comp:31-60 */
+void gso_emit_keys(const gso_attr *attr, const uint32_t *scan, uint64_t n, uint32_t tileX,
+                   uint64_t *keys, uint32_t *vals) {
+    for (uint64_t i = 0; i < n; i++) {
+        const gso_attr *a = &attr[i];
+        if (a->color_radii[3] == 0.0f) continue;  /* :37-39 */
+        uint32_t ind = i == 0 ? 0 : scan[i - 1]; /* :43 */
+        uint32_t depth_bits;
+        memcpy(&depth_bits, &a->depth, 4); /* floatBitsToUint :52 */
+        for (uint32_t x = a->aabb[0]; x < a->aabb[2]; x++)       /* :47 */
+            for (uint32_t y = a->aabb[1]; y < a->aabb[3]; y++) { /* :48 */
+                uint64_t tile_index = (uint64_t)(x + y * tileX); /* :49 (uint arithmetic, then widened) */
+                keys[ind] = (tile_index << 32) | (uint64_t)depth_bits;
+                vals[ind] = (uint32_t)i;
+                ind++;
+            }
+        /* :60 assert(ind == prefixSum[index]) */
+        if (ind != scan[i]) {
+            fprintf(stderr, "gs_oracle: emit invariant violated at %llu\n", (unsigned long long)i);
+            abort();
+        }
+    }
+}
+
+/* A6. 8 x (hist.comp + sort.comp): stable LSD radix on 8-bit digits over all 64 key bits. */
+void gso_sort(uint64_t *keys, uint32_t *vals, uint64_t m) {
+    if (m == 0) return;
+    uint64_t *k2 = (uint64_t *)malloc((size_t)m * 8);
+    uint32_t *v2 = (uint32_t *)malloc((size_t)m * 4);
+    uint64_t *ks = keys, *kd = k2;
+    uint32_t *vs = vals, *vd = v2;
+    for (int pass = 0; pass < 8; pass++) { /* Renderer.cpp:598 */
+        const int shift = 8 * pass;
+        uint64_t hist[256] = {0};
+        for (uint64_t i = 0; i < m; i++) hist[(ks[i] >> shift) & 255]++;
+        uint64_t sum = 0;
+        for (int b = 0; b < 256; b++) {
+            uint64_t c = hist[b];
+            hist[b] = sum;
+            sum += c;
+        }
+        for (uint64_t i = 0; i < m; i++) {
+            uint64_t p = hist[(ks[i] >> shift) & 255]++;
+            kd[p] = ks[i];
+            vd[p] = vs[i];
+        }
+        uint64_t *tk = ks;
+        ks = kd;
+        kd = tk;
+        uint32_t *tv = vs;
+        vs = vd;
+        vd = tv;
+    }
+    /* 8 passes: result is back in the caller's ("Even") buffers, Renderer.cpp:641 */
+    free(k2);
+    free(v2);
+}
+
+/* A7. tile_boundary.comp:22-50 */
+void gso_tile_ranges(const uint64_t *keys, uint64_t m, uint32_t num_tiles, uint32_t *ranges) {
+    memset(ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t)); /* Renderer.cpp:633 */
+    for (uint64_t i = 0; i < m; i++) {
+        uint32_t key = (uint32_t)(keys[i] >> 32);
+        if (i == 0) {
+            ranges[key * 2] = (uint32_t)i;
+        } else {
+            uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+            if (key != prev) {
+                ranges[key * 2] = (uint32_t)i;
+                ranges[prev * 2 + 1] = (uint32_t)i;
+            }
+        }
+        if (i == m - 1) ranges[key * 2 + 1] = (uint32_t)m;
+    }
+}
+
+/* A8. render.comp:30-99 */
+void gso_blend(const gso_attr *attr, const uint32_t *vals, const uint32_t *ranges, uint32_t width,
+               uint32_t height, uint32_t tile_row_begin, uint32_t tile_row_end, float *rgba,
+               uint32_t *consumed) {
+    const uint32_t tiles_x = (width + TILE_W - 1) / TILE_W;
+    const uint32_t tiles_y = (height + TILE_H - 1) / TILE_H;
+    if (tile_row_end > tiles_y) tile_row_end = tiles_y;
+    const int exp_mode = g_exp_mode;
+    const int64_t t0 = (int64_t)tile_row_begin * tiles_x, t1 = (int64_t)tile_row_end * tiles_x;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4)
+#endif
+    for (int64_t tt = t0; tt < t1; tt++) {
+        const uint32_t tile_x = (uint32_t)(tt % tiles_x), tile_y = (uint32_t)(tt / tiles_x);
+        const uint32_t start = ranges[tt * 2], end = ranges[tt * 2 + 1]; /* :43-44 */
+        uint32_t max_consumed = 0;
+        for (uint32_t ly = 0; ly < TILE_H; ly++)
+            for (uint32_t lx = 0; lx < TILE_W; lx++) {
+                const uint32_t px = tile_x * TILE_W + lx, py = tile_y * TILE_H + ly; /* :36 */
+                if (px >= width || py >= height) continue;                           /* :37-39 */
+                float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+                const float fx = (float)px, fy = (float)py;
+                uint32_t i;
+                for (i = start; i < end; i++) { /* :61 */
+                    const gso_attr *a = &attr[vals[i]];
+                    float dx = a->uv[0] - fx, dy = a->uv[1] - fy; /* :64 */
+                    const float *co = a->conic_opacity;
+                    float power = -0.5f * ((co[0] * dx) * dx + (co[2] * dy) * dy) - (co[1] * dx) * dy; /* :66 */
+                    if (power > 0.0f) continue; /* :68-70 */
+                    float e;
+                    if (exp_mode == 1) {
+                        if (power < -5.55f) continue; /* alpha <= exp(-5.55) < 1/255 since opacity <= 1 */
+                        e = gso_exp_shared(power);
+                    } else {
+                        e = expf(power);
+                    }
+                    float alpha = fminf(0.99f, co[3] * e); /* :77 */
+                    if (alpha < 1.0f / 255.0f) continue;   /* :78-80 */
+                    float test_T = T * (1.0f - alpha);     /* :82 */
+                    if (test_T < 0.0001f) break;           /* :83-85 */
+                    c0 = c0 + (a->color_radii[0] * alpha) * T; /* :87 */
+                    c1 = c1 + (a->color_radii[1] * alpha) * T;
+                    c2 = c2 + (a->color_radii[2] * alpha) * T;
+                    T = test_T; /* :88 */
+                }
+                uint32_t used = (i < end ? i + 1 : end) - start;
+                if (used > max_consumed) max_consumed = used;
+                float *o = rgba + ((size_t)py * width + px) * 4;
+                o[0] = c0;
+                o[1] = c1;
+                o[2] = c2;
+                o[3] = 1.0f; /* :98 vec4(c, 1.0) -- no background term */
+            }
+        if (consumed) consumed[tt] = max_consumed;
+    }
+}
+
+void gso_pack_unorm8(const float *rgba, uint64_t npix, int bgra, uint8_t *out) {
+    for (uint64_t i = 0; i < npix; i++) {
+        uint8_t q[4];
+        for (int c = 0; c < 4; c++) {
+            float v = rgba[i * 4 + c];
+            if (!(v > 0.0f)) v = 0.0f; /* NaN -> 0 */
+            if (v > 1.0f) v = 1.0f;
+            q[c] = (uint8_t)lrintf(v * 255.0f); /* round to nearest even */
+        }
+        if (bgra) {
+            out[i * 4 + 0] = q[2];
+            out[i * 4 + 1] = q[1];
+            out[i * 4 + 2] = q[0];
+        } else {
+            out[i * 4 + 0] = q[0];
+            out[i * 4 + 1] = q[1];
+            out[i * 4 + 2] = q[2];
+        }
+        out[i * 4 + 3] = q[3];
+    }
+}
+
+/* Renderer::draw() order, src/Renderer.cpp:366-426 */
+int gso_render_frame(const float *vtx, const float *cov, uint64_t n, const gso_uniforms *u,
+                     uint32_t tile_row_begin, uint32_t tile_row_end, gso_frame *f) {
+    memset(f, 0, sizeof *f);
+    f->n = n;
+    f->width = u->width;
+    f->height = u->height;
+    f->tiles_x = (u->width + TILE_W - 1) / TILE_W;
+    f->tiles_y = (u->height + TILE_H - 1) / TILE_H;
+    const uint32_t T = f->tiles_x * f->tiles_y;
+    f->attr = (gso_attr *)malloc((size_t)(n ? n : 1) * sizeof(gso_attr));
+    f->tiles = (uint32_t *)malloc((size_t)(n ? n : 1) * 4);
+    f->scan = (uint32_t *)malloc((size_t)(n ? n : 1) * 4);
+    f->ranges = (uint32_t *)malloc((size_t)(T ? T : 1) * 8);
+    f->consumed = (uint32_t *)calloc((size_t)(T ? T : 1), 4);
+    f->rgba = (float *)calloc((size_t)u->width * u->height * 4 + 4, sizeof(float));
+    if (!f->attr || !f->tiles || !f->scan || !f->ranges || !f->consumed || !f->rgba) return -1;
+
+    double t = now_s(), t2;
+    gso_preprocess(vtx, cov, n, u, tile_row_begin, tile_row_end, f->attr, f->tiles);
+    t2 = now_s();
+    f->t_stage[0] = t2 - t;
+    t = t2;
+    f->m = gso_scan_inclusive(f->tiles, n, f->scan);
+    t2 = now_s();
+    f->t_stage[1] = t2 - t;
+    t = t2;
+    const size_t mm = (size_t)(f->m ? f->m : 1);
+    f->keys = (uint64_t *)malloc(mm * 8);
+    f->vals = (uint32_t *)malloc(mm * 4);
+    f->keys_unsorted = (uint64_t *)malloc(mm * 8);
+    f->vals_unsorted = (uint32_t *)malloc(mm * 4);
+    if (!f->keys || !f->vals || !f->keys_unsorted || !f->vals_unsorted) return -1;
+    gso_emit_keys(f->attr, f->scan, n, f->tiles_x, f->keys, f->vals);
+    t2 = now_s();
+    f->t_stage[2] = t2 - t;
+    memcpy(f->keys_unsorted, f->keys, (size_t)f->m * 8);
+    memcpy(f->vals_unsorted, f->vals, (size_t)f->m * 4);
+    t = now_s();
+    gso_sort(f->keys, f->vals, f->m);
+    t2 = now_s();
+    f->t_stage[3] = t2 - t;
+    t = t2;
+    gso_tile_ranges(f->keys, f->m, T, f->ranges);
+    t2 = now_s();
+    f->t_stage[4] = t2 - t;
+    t = t2;
+    gso_blend(f->attr, f->vals, f->ranges, u->width, u->height, tile_row_begin, tile_row_end, f->rgba,
+              f->consumed);
+    t2 = now_s();
+    f->t_stage[5] = t2 - t;
+    return 0;
+}
+
+void gso_frame_free(gso_frame *f) {
+    free(f->attr);
+    free(f->tiles);
+    free(f->scan);
+    free(f->keys);
+    free(f->vals);
+    free(f->keys_unsorted);
+    free(f->vals_unsorted);
+    free(f->ranges);
+    free(f->consumed);
+    free(f->rgba);
+    memset(f, 0, sizeof *f);
+}
