@@ -214,6 +214,16 @@ def synth_records(seed: int, n: int, params: SynthParams | None = None, first: i
     return out
 
 
+def band_for_rank(height: int, rank: int, world: int):
+    """Tile-row band [begin, end) of `rank` for frame sharding: equal-height bands of
+    R = ceil(ceil(H/16) / world) tile rows (NCCL all-gather needs equal counts); trailing ranks may be
+    short or empty.  Returns (begin, end, rows_per_rank)."""
+    tiles_y = (height + 15) // 16
+    rows_per = (tiles_y + world - 1) // world
+    begin = min(tiles_y, rank * rows_per)
+    return begin, min(tiles_y, begin + rows_per), rows_per
+
+
 def stream_ptr(stream=None):
     """cudaStream_t of a torch stream (or None -> the context's own stream)."""
     return None if stream is None else C.c_void_p(stream.cuda_stream)

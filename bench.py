@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the 3DGS forward hot path (project+SH -> bin -> sort -> blend) on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line
+(rank 0).  A "step" is one frame of the hot path.  Workload at N=1: BASELINE.json's headline config
+(garden, 5.8 M Gaussians, 3200x1400) as a SYNTHETIC STAND-IN (the Inria .ply files are not
+available offline): 5.8 M seeded Gaussians tuned to M/N ~ 5.
+
+  value : frames/s with the camera UBO as a kernel argument and the framebuffer left in HBM
+          (K frames enqueued back to back on one stream, CUDA events around them, max over ranks).
+  e2e   : frames/s through the public C ABI call gsb_render() with HOST buffers: host UBO in,
+          B8G8R8A8 framebuffer (the reference's swapchain format) copied device->host inside the
+          timed region every step, synchronous per frame.
+  N > 1 : the frame is sharded by tile rows over N GPUs (one process per GPU, scene replicated),
+          each rank renders its band, one NCCL all-gather reassembles the framebuffer
+          (strong scaling: total work fixed).
+  --impl reference : the reference has no CPU path and its Vulkan build is unavailable here, so
+          the reference arm times the CPU oracle (oracle/, "port") on the box's host cores on a
+          bounded sample (a band of tile rows of the same frame) and extrapolates frames/s.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "3dgs.cpp_b200" / "python"))
+
+WORKLOADS = {
+    # name: N, W, H, seed, synth params, camera (pos, fov)
+    "garden-standin": dict(n=5_800_000, w=3200, h=1400, seed=3, half=(10.0, 4.0, 10.0), ls=(0.003, 0.05),
+                           cam=(0.0, 0.0, 14.0), fov=45.0,
+                           note="synthetic stand-in for Mip-NeRF360 garden (5.8M Gaussians, 3200x1400), M/N~5"),
+    "bicycle-standin": dict(n=6_100_000, w=1920, h=1080, seed=4, half=(10.0, 5.6, 10.0), ls=(0.003, 0.05),
+                            cam=(0.0, 0.0, 14.0), fov=45.0, note="synthetic stand-in for bicycle (6.1M, 1920x1080)"),
+    "truck-standin": dict(n=2_500_000, w=3840, h=2160, seed=5, half=(10.0, 5.6, 10.0), ls=(0.003, 0.05),
+                          cam=(0.0, 0.0, 14.0), fov=45.0, note="synthetic stand-in for truck (2.5M, 3840x2160)"),
+    "synthetic-50m": dict(n=50_000_000, w=7680, h=4320, seed=43, half=(10.0, 5.6, 10.0), ls=(0.002, 0.03),
+                          cam=(0.0, 0.0, 14.0), fov=45.0, note="BASELINE config 5: synthetic 50M, 7680x4320"),
+    "c1": dict(n=10_000, w=640, h=480, seed=42, half=(3.0, 3.0, 3.0), ls=(0.01, 0.15), cam=(0.0, 0.0, 5.0), fov=45.0,
+               note="BASELINE config 1: synthetic 10k, 640x480"),
+}
+NUM_CAMERAS = 8  # small orbit so consecutive frames differ (M varies a few %)
+
+
+def make_scene(g, wl):
+    p = g.synth_params(center=(0, 0, 0), half_extent=wl["half"], log_scale_min=math.log(wl["ls"][0]),
+                       log_scale_max=math.log(wl["ls"][1]))
+    n = wl["n"]
+    vtx = np.empty((n, 60), np.float32)
+    chunk = 1 << 20
+    for off in range(0, n, chunk):  # PLY-format records -> GSScene::load activations (C++ host)
+        cnt = min(chunk, n - off)
+        vtx[off:off + cnt] = g.activate_records(g.synth_records(wl["seed"], cnt, p, first=off))
+    return vtx
+
+
+def cameras(g, wl):
+    cams = []
+    for k in range(NUM_CAMERAS):
+        a = math.radians(-6.0 + 12.0 * k / max(1, NUM_CAMERAS - 1))  # +-6 degree orbit around the scene centre
+        d = wl["cam"][2]
+        pos = (d * math.sin(a), wl["cam"][1], d * math.cos(a))
+        quat = (math.cos(a / 2), 0.0, math.sin(a / 2), 0.0)  # yaw so the camera keeps looking at the origin
+        cams.append(g.uniforms_from_camera(pos, quat, wl["fov"], 0.1, 1000.0, wl["w"], wl["h"]))
+    return cams
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_oracle_sample(wl, vtx, u, budget_s):
+    """Times the CPU oracle on a bounded sample: all N Gaussians preprocessed, but only a centred band
+    of tile rows sorted + blended; frames/s is extrapolated by rows_total / rows_band for the
+    band-proportional stages."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle as o
+
+    cov = o.cov3d(vtx)
+    tiles_y = (wl["h"] + 15) // 16
+    rows = 1
+    mid = tiles_y // 2
+    t0 = time.perf_counter()
+    f = o.render_frame(vtx, cov, u, rows=(mid, mid + 1))  # calibration
+    t_cal = time.perf_counter() - t0
+    t_pre = f["t_stage"]["preprocess"] + f["t_stage"]["prefix_sum"]
+    t_row = max(1e-6, t_cal - t_pre)
+    rows = int(max(1, min(tiles_y, (budget_s - t_pre) // t_row)))
+    rb = max(0, mid - rows // 2)
+    re = min(tiles_y, rb + rows)
+    t0 = time.perf_counter()
+    f = o.render_frame(vtx, cov, u, rows=(rb, re))
+    wall = time.perf_counter() - t0
+    st = f["t_stage"]
+    full_pre = st["preprocess"] + st["prefix_sum"]
+    banded = st["preprocess_sort"] + st["sort"] + st["tile_boundary"] + st["render"]
+    t_frame = full_pre + banded * tiles_y / (re - rb)
+    return {"fps": 1.0 / t_frame, "t_frame_s": t_frame, "sample_wall_s": wall, "rows": (rb, re), "tiles_y": tiles_y,
+            "cores": o.num_threads(), "m_band": int(f["m"]), "stages_s": st}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE {world}")
+    wl_name = args.workload or "garden-standin"
+    wl = WORKLOADS[wl_name]
+
+    import gs_b200 as g  # raises if the CUDA library is not built: no fallback
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vtx = make_scene(g, wl)
+        cams = cameras(g, wl)
+        total = max(1, args.steps + args.warmup)
+        per_step = max(2.0, min(30.0, 150.0 / total))
+        vals = []
+        for s in range(total):
+            r = cpu_oracle_sample(wl, vtx, cams[s % NUM_CAMERAS], per_step)
+            if s >= args.warmup:
+                vals.append(r)
+        fps = float(np.mean([r["fps"] for r in vals]))
+        sample = (f"per step: all {wl['n']} Gaussians preprocessed, tile rows {vals[-1]['rows']} of {vals[-1]['tiles_y']} "
+                  f"sorted+blended (~{vals[-1]['sample_wall_s']:.1f}s), frames/s extrapolated by rows_total/rows_band")
+        print(json.dumps({
+            "impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / fps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "note": wl["note"], "n_gaussians": wl["n"], "width": wl["w"], "height": wl["h"]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[-1]["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference (Vulkan/GLSL) has no CPU path and cannot be built offline; this is the CPU oracle port",
+        }))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    vtx = make_scene(g, wl)
+    cams = cameras(g, wl)
+    W, H = wl["w"], wl["h"]
+    tiles_y = (H + 15) // 16
+    rb, re, rows_per = g.band_for_rank(H, rank, world)  # equal-height bands (all-gather needs equal counts)
+    band = (rb, re) if world > 1 else None
+
+    ctx = g.Context(local_rank)
+    ctx.set_mode(g.MODE_EXACT if args.mode == "exact" else g.MODE_FAST)
+    ctx.upload(vtx)
+    fmt, bpp = g.FORMAT_BGRA8, 4
+    band_buf = torch.zeros((rows_per * 16, W, bpp), dtype=torch.uint8, device=dev)
+    full_buf = torch.zeros((world * rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) if world > 1 else band_buf
+    stream = torch.cuda.current_stream()
+
+    # first frame sizes the instance arena (regrow path), then keep 25% headroom for the orbit
+    ctx.render_into(cams[0], band_buf.data_ptr(), fmt, rows=band, stream=stream, sync=True)
+    st0 = ctx.stats()
+    ctx.reserve(int(st0.num_instances * 1.3) + 65536)
+
+    def frame(i, sync):
+        if rb < re:
+            ctx.render_into(cams[i % NUM_CAMERAS], band_buf.data_ptr(), fmt, rows=band, stream=stream, sync=sync)
+        if world > 1:
+            dist.all_gather_into_tensor(full_buf.view(-1), band_buf.view(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        frame(i, sync=True)
+
+    # per-stage / per-kernel times (library cudaEvents), sampled on separate untimed frames
+    stage_acc, m_acc, cons_acc, vis_acc = {}, [], [], []
+    for i in range(NUM_CAMERAS):
+        frame(i, sync=True)
+        s = ctx.stats()
+        d = s.as_dict()
+        for k in ("preprocess_ms", "sort_ms", "tile_boundary_ms", "render_ms", "frame_ms", "sort_hist_ms"):
+            stage_acc.setdefault(k, []).append(d[k])
+        stage_acc.setdefault("sort_pass_ms", []).append(float(np.mean(d["sort_pass_ms"])) if d["sort_pass_ms"] else 0.0)
+        m_acc.append(s.num_instances)
+        cons_acc.append(s.blend_consumed)
+        vis_acc.append(s.num_visible)
+        passes = s.sort_passes
+    stage = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    M, NV, CONS = float(np.mean(m_acc)), float(np.mean(vis_acc)), float(np.mean(cons_acc))
+
+    # ---- value: K frames, device resident, one stream, CUDA events, max over ranks ----
+    ctx.set_timers(False)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        frame(i, sync=False)
+    e1.record(stream)
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / args.steps
+    ovf = ctx.stats()  # raises GSB_ERR_OVERFLOW if any async frame overflowed the arena
+    del ovf
+
+    # ---- e2e: public C-ABI call with HOST buffers (UBO H2D + framebuffer D2H every step) ----
+    nrows = min(H, re * 16) - rb * 16 if rb < re else 0
+    host_fb = torch.empty((max(nrows, 1), W, bpp), dtype=torch.uint8).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        if nrows:
+            ctx._ck(g.lib.gsb_render(ctx.h, cams[i % NUM_CAMERAS], rb, re, host_fb.data_ptr(), 0, g.MEM_HOST, fmt, None))
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_fps = args.steps / float(e2e_s.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        nv = NV
+        # algorithmic bytes per launch (SURVEY 8d / DESIGN.md), one launch = one frame's worth of that kernel
+        alg = {
+            "k_preprocess": wl["n"] * 40 + nv * 192 + nv * 48 + 12 * M,       # scene read + SH of survivors + 48-B records + keys/payloads
+            "k_sort_hist": 8 * M,
+            "k_onesweep_pass": 24 * M,                                        # 12 B read + 12 B written per key
+            "k_tile_ranges": 8 * M + 8 * ((W + 15) // 16) * tiles_y,
+            "k_blend": CONS * (4 + 36) + (nrows if world == 1 else H) * W * bpp,
+        }
+        dur = {"k_preprocess": stage["preprocess_ms"], "k_sort_hist": stage["sort_hist_ms"],
+               "k_onesweep_pass": stage["sort_pass_ms"], "k_tile_ranges": stage["tile_boundary_ms"], "k_blend": stage["render_ms"]}
+        share = {"k_preprocess": stage["preprocess_ms"], "k_sort_hist": stage["sort_hist_ms"],
+                 "k_onesweep_pass": stage["sort_pass_ms"] * passes, "k_tile_ranges": stage["tile_boundary_ms"],
+                 "k_blend": stage["render_ms"]}
+        kern = {k: {"ms_per_launch": dur[k], "launches_per_step": passes if k == "k_onesweep_pass" else 1,
+                    "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (dur[k] * 1e-3) / 1e9 if dur[k] > 0 else None,
+                    "share_of_step": share[k] / stage["frame_ms"] if stage["frame_ms"] > 0 else None} for k in alg}
+        dom = max(share, key=share.get)
+        roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["achieved_gbs"] / peak if kern[dom]["achieved_gbs"] else None, "traffic": None,
+                "peak_source": peak_src,
+                "note": "k_blend is FP32/SFU-issue bound (SURVEY 8d): its HBM fraction is reported as required, pair-evals/s beside it"}
+        out = {
+            "metric": "frames/sec", "value": 1000.0 / ms_step, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "note": wl["note"], "n_gaussians": wl["n"], "width": W, "height": H,
+                       "instances_M": M, "visible": NV, "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8",
+                       "cameras": NUM_CAMERAS, "l2": "inputs (1.3 GB scene + 0.4 GB keys) larger than the 126 MB L2; no flush",
+                       "parallelism": f"tile-row bands x{world}" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 160,
+                    "d2h_bytes_per_step": int(nrows * W * bpp) + 64, "api": "gsb_render(host UBO -> host BGRA8), synchronous per frame"},
+            "gpu_launches": int((4 + passes) * args.steps),
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": kern,
+            "stage_ms": stage,
+            "sort_keys_per_s": M / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
+            "blend_pair_evals_per_s": CONS * 256 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_oracle_sample(wl, vtx, cams[0], 20.0)
+            out["cpu_baseline"] = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                                   "sample": f"all {wl['n']} Gaussians preprocessed, tile rows {r['rows']} of {r['tiles_y']} sorted+blended "
+                                             f"({r['sample_wall_s']:.1f}s wall), extrapolated by rows_total/rows_band"}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -71,6 +71,8 @@ lib.gso_render_frame.restype = C.c_int
 lib.gso_frame_free.argtypes = [C.POINTER(Frame)]
 lib.gso_frame_free.restype = None
 lib.gso_num_threads.restype = C.c_int
+lib.gso_preprocess.argtypes = [_vp, _vp, C.c_uint64, C.POINTER(Uniforms), C.c_uint32, C.c_uint32, _vp, _vp]
+lib.gso_preprocess.restype = None
 
 STAGES = ["preprocess", "prefix_sum", "preprocess_sort", "sort", "tile_boundary", "render"]
 ALL_ROWS = 0xFFFFFFFF
@@ -142,6 +144,18 @@ def sort_pairs(keys, vals):
     v = np.ascontiguousarray(vals, np.uint32).copy()
     lib.gso_sort(k.ctypes.data, v.ctypes.data, k.size)
     return k, v
+
+
+def preprocess(vertices, cov, u, rows=None):
+    """A3 only (preprocess.comp): returns (attr, tiles_overlap)."""
+    v = _f32(vertices).reshape(-1, 60)
+    cv = _f32(cov).reshape(-1, 6)
+    ou = Uniforms.from_buffer_copy(bytes(u))
+    rb, re = (0, ALL_ROWS) if rows is None else rows
+    attr = np.zeros(v.shape[0], ATTR_DTYPE)
+    tiles = np.zeros(v.shape[0], np.uint32)
+    lib.gso_preprocess(v.ctypes.data, cv.ctypes.data, v.shape[0], C.byref(ou), rb, re, attr.ctypes.data, tiles.ctypes.data)
+    return attr, tiles
 
 
 def uniforms_bytes(u) -> bytes:
