@@ -14,9 +14,9 @@ namespace gsb {
 
 namespace {
 
-constexpr int SORT_THREADS = 256;
+constexpr int SORT_THREADS = 512;
 constexpr int SORT_IPT = 16;                          // keys per thread
-constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;   // 4096 keys per tile
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;   // 8192 keys per tile
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
 constexpr unsigned FULL = 0xffffffffu;
@@ -66,10 +66,15 @@ __global__ void __launch_bounds__(HIST_THREADS) k_sort_hist(const unsigned long 
             for (int p = 0; p < P; p++) {
                 const uint32_t d = (uint32_t)(k[it] >> (8 * p)) & 255u;
                 if (p >= 3) {
-                    // upper digits (depth exponent byte, tile id) are heavily skewed: aggregate equal
-                    // digits inside the warp so a hot bin costs one shared atomic, not 32 serialised ones
-                    const unsigned peers = __match_any_sync(FULL, valid ? d : 0xffffffffu);
-                    if (valid && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
+                    // upper digits (depth exponent byte, tile id) are skewed: lanes that share lane 0's digit are
+                    // counted with one ballot and a single shared atomic instead of up to 32 serialised ones
+                    const uint32_t d0 = __shfl_sync(FULL, d, 0);
+                    const unsigned same = __ballot_sync(FULL, valid && d == d0);
+                    if ((threadIdx.x & 31) == 0) {
+                        if (same) atomicAdd(&s_hist[p][d0], (uint32_t)__popc(same));
+                    } else if (valid && d != d0) {
+                        atomicAdd(&s_hist[p][d], 1u);
+                    }
                 } else if (valid) {
                     atomicAdd(&s_hist[p][d], 1u);
                 }
@@ -85,22 +90,61 @@ __global__ void __launch_bounds__(HIST_THREADS) k_sort_hist(const unsigned long 
 
 // ------------------------------------------------------------------------------------------
 // One Onesweep pass (replaces one hist.comp + sort.comp pair).
+//
+// Persistent kernel, ONE 512-thread CTA per SM, tile = 8192 pairs (64 KB keys + 32 KB payloads).
+//  * TMA: the next tile's keys and payloads are fetched by cp.async.bulk (UBLKCP) into the second
+//    shared-memory buffer while the current tile is ranked and scattered; completion is an
+//    mbarrier transaction count.  No registers are tied up by loads in flight.
+//  * ranking: warp-striped, match.any per 8-bit digit, per-warp digit counters in smem (stable).
+//  * the tile is permuted IN PLACE in shared memory (raw -> digit-sorted), so the global scatter
+//    writes runs of consecutive addresses per digit (coalesced 8-B key / 4-B payload stores).
+//  * chained scan: tile aggregate published right after ranking, decoupled look-back per digit
+//    with a window of LB_WINDOW predecessors in flight, done after the in-place permutation so
+//    the predecessors' latency overlaps local work.
 // ------------------------------------------------------------------------------------------
-struct PassSmem {
-    union {
-        unsigned long long keys[SORT_TILE];  // 32 KB
-        uint32_t vals[SORT_TILE];
-    };
-    uint32_t whist[SORT_WARPS][RADIX];  // per-warp digit counters -> exclusive offsets across warps
-    uint32_t bin_start[RADIX];          // exclusive scan of the tile's digit counts
-    int32_t out_base[RADIX];            // global index of bin d's first element minus bin_start[d]
-    uint32_t gexcl[RADIX];              // exclusive scan of the global histogram of this pass
-    uint32_t warp_sums[SORT_WARPS];
-    uint32_t tile;
-};
+constexpr int LB_WINDOW = 4;
 
-// exclusive scan of one value per thread across the 256-thread block
-__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* warp_sums, uint32_t* total) {
+struct PassSmem {
+    unsigned long long keys[2][SORT_TILE];  // 2 x 64 KB (double buffer: current / prefetch)
+    uint32_t vals[2][SORT_TILE];            // 2 x 32 KB
+    uint32_t whist[SORT_WARPS][RADIX];      // per-warp digit counters -> exclusive offsets across warps
+    uint32_t bin_start[RADIX];              // exclusive scan of the tile's digit counts
+    int32_t out_base[RADIX];                // global index of bin d's first element minus bin_start[d]
+    uint32_t gexcl[RADIX];                  // exclusive scan of the global histogram of this pass
+    uint32_t warp_sums[SORT_WARPS];
+    unsigned long long mbar[2];             // TMA completion barriers, one per buffer
+    uint32_t tile[2];                       // ticket held by each buffer
+};
+static_assert(sizeof(PassSmem) <= 227 * 1024, "PassSmem exceeds the 227 KB per-CTA shared memory of sm_100");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// exclusive scan of one value per thread across the block (NW warps)
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_sums) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = v;
 #pragma unroll
@@ -110,24 +154,22 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* wa
     }
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    uint32_t before = 0, tot = 0;
+    uint32_t before = 0;
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) {
+    for (int w = 0; w < NW; w++) {
         const uint32_t s = warp_sums[w];
         if (w < warp) before += s;
-        tot += s;
     }
     __syncthreads();
-    if (total) *total = tot;
     return before + incl - v;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS, 2)
+__global__ void __launch_bounds__(SORT_THREADS, 1)
     k_onesweep_pass(const unsigned long long* __restrict__ kin, const uint32_t* __restrict__ vin,
                     unsigned long long* __restrict__ kout, uint32_t* __restrict__ vout,
                     const uint32_t* __restrict__ d_m, Control* ctl, int pass, unsigned long long* status,
                     uint32_t status_tiles, uint32_t epoch) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     PassSmem& S = *reinterpret_cast<PassSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = 8 * pass;
@@ -136,39 +178,65 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
     if (num_tiles > status_tiles) num_tiles = status_tiles;  // host sizes status for the arena capacity
     const unsigned long long epoch_hi = (unsigned long long)epoch << 32;
 
+    auto fetch = [&](int buf) {  // thread 0: take the next ticket and start its TMA loads into `buf`
+        const uint32_t t = atomicAdd(&ctl->sort_ticket[pass], 1u);
+        S.tile[buf] = t;
+        if (t < num_tiles && m - t * SORT_TILE >= (uint32_t)SORT_TILE) {  // full tile: TMA; the ragged last tile is loaded by the threads
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy accesses to `buf` are done (barrier) -> async proxy may write
+            mbar_expect_tx(&S.mbar[buf], SORT_TILE * 12);
+            tma_load(S.keys[buf], kin + (size_t)t * SORT_TILE, SORT_TILE * 8, &S.mbar[buf]);
+            tma_load(S.vals[buf], vin + (size_t)t * SORT_TILE, SORT_TILE * 4, &S.mbar[buf]);
+        }
+    };
+
+    if (tid == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // exclusive prefix of the global histogram of this digit (thread d <-> bin d)
     {
-        const uint32_t c = ctl->hist[pass][tid];
-        S.gexcl[tid] = block_excl_scan_256(c, S.warp_sums, nullptr);
+        const uint32_t c = tid < RADIX ? ctl->hist[pass][tid] : 0u;
+        const uint32_t ex = block_excl_scan<SORT_WARPS>(c, S.warp_sums);
+        if (tid < RADIX) S.gexcl[tid] = ex;
     }
+    if (tid == 0) fetch(0);
+    __syncthreads();
 
+    int cur = 0;
+    uint32_t parity[2] = {0u, 0u};
     while (true) {
-        if (tid == 0) S.tile = atomicAdd(&ctl->sort_ticket[pass], 1u);
-        // zero the per-warp counters
-#pragma unroll
-        for (int k = 0; k < SORT_WARPS; k++) S.whist[k][tid] = 0;
-        __syncthreads();
-        const uint32_t tile = S.tile;
+        const uint32_t tile = S.tile[cur];
         if (tile >= num_tiles) break;
+        if (tid == 0) fetch(cur ^ 1);  // buffer cur^1 was released by the barrier that ended the previous iteration
         const uint32_t tile_base = tile * SORT_TILE;
         const uint32_t valid = min((uint32_t)SORT_TILE, m - tile_base);
+        unsigned long long* sk = S.keys[cur];
+        uint32_t* sv = S.vals[cur];
 
-        // ---- load: warp-striped so that (warp, round, lane) order == memory order ----
-        unsigned long long key[SORT_IPT];
-        uint32_t val[SORT_IPT];
+        // zero the per-warp counters (16 x 256 words, 8 per thread)
 #pragma unroll
-        for (int it = 0; it < SORT_IPT; it++) {
-            const uint32_t li = warp * (32 * SORT_IPT) + it * 32 + lane;
-            const bool ok = li < valid;
-            key[it] = ok ? __ldg(kin + tile_base + li) : ~0ull;
-            val[it] = ok ? __ldg(vin + tile_base + li) : 0u;
+        for (int k = 0; k < SORT_WARPS * RADIX / SORT_THREADS; k++) (&S.whist[0][0])[k * SORT_THREADS + tid] = 0;
+        if (valid == (uint32_t)SORT_TILE) {
+            mbar_wait(&S.mbar[cur], parity[cur]);
+            parity[cur] ^= 1u;
+        } else {  // ragged last tile: plain loads, padded with the maximum key so the padding sorts last
+#pragma unroll 4
+            for (int it = 0; it < SORT_IPT; it++) {
+                const uint32_t li = it * SORT_THREADS + tid;
+                const bool ok = li < valid;
+                sk[li] = ok ? __ldg(kin + tile_base + li) : ~0ull;
+                sv[li] = ok ? __ldg(vin + tile_base + li) : 0u;
+            }
         }
+        __syncthreads();
 
-        // ---- rank inside the warp (stable): match equal digits, count predecessors ----
-        uint32_t rank[SORT_IPT];  // rank within (warp, digit)
+        // ---- rank inside the warp (stable): warp-striped so (warp, round, lane) order == memory order ----
+        const uint32_t wbase = warp * (32 * SORT_IPT) + lane;
+        uint16_t rank[SORT_IPT];
 #pragma unroll
         for (int it = 0; it < SORT_IPT; it++) {
-            const uint32_t d = (uint32_t)(key[it] >> shift) & 255u;
+            const uint32_t d = (uint32_t)(sk[wbase + it * 32] >> shift) & 255u;
             const unsigned peers = __match_any_sync(FULL, d);
             const int leader = __ffs(peers) - 1;
             uint32_t prev = 0;
@@ -177,72 +245,83 @@ __global__ void __launch_bounds__(SORT_THREADS, 2)
                 S.whist[warp][d] = prev + __popc(peers);
             }
             prev = __shfl_sync(FULL, prev, leader);
-            rank[it] = prev + __popc(peers & ((1u << lane) - 1u));
+            rank[it] = (uint16_t)(prev + __popc(peers & ((1u << lane) - 1u)));
             __syncwarp();
         }
         __syncthreads();
 
-        // ---- per digit (thread d): exclusive scan across warps, tile count ----
+        // ---- per digit (thread d < 256): exclusive scan across warps, tile count, publish the aggregate ----
         uint32_t count = 0;
+        if (tid < RADIX) {
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++) {
-            const uint32_t c = S.whist[w][tid];
-            S.whist[w][tid] = count;
-            count += c;
-        }
-        // publish the tile aggregate (tile 0 has no predecessors: inclusive prefix right away)
-        st_volatile(status + (size_t)tile * RADIX + tid, epoch_hi | (tile == 0 ? LB_PREFIX : LB_AGG) | count);
-
-        const uint32_t bstart = block_excl_scan_256(count, S.warp_sums, nullptr);
-        S.bin_start[tid] = bstart;
-
-        // ---- decoupled look-back for digit `tid` ----
-        uint32_t excl = 0;
-        if (tile != 0) {
-            int t = (int)tile - 1;
-            while (true) {
-                const unsigned long long w = ld_volatile(status + (size_t)t * RADIX + tid);
-                if ((w >> 32) != epoch) continue;  // not yet published in this pass
-                const uint32_t lo = (uint32_t)w;
-                if ((lo & (LB_AGG | LB_PREFIX)) == 0) continue;
-                excl += lo & LB_COUNT;
-                if (lo & LB_PREFIX) break;
-                --t;
+            for (int w = 0; w < SORT_WARPS; w++) {
+                const uint32_t c = S.whist[w][tid];
+                S.whist[w][tid] = count;
+                count += c;
             }
-            st_volatile(status + (size_t)tile * RADIX + tid, epoch_hi | LB_PREFIX | (excl + count));
+            // tile 0 has no predecessors: inclusive prefix right away
+            st_volatile(status + (size_t)tile * RADIX + tid, epoch_hi | (tile == 0 ? LB_PREFIX : LB_AGG) | count);
         }
-        S.out_base[tid] = (int32_t)(S.gexcl[tid] + excl) - (int32_t)bstart;
+        const uint32_t bstart = block_excl_scan<SORT_WARPS>(count, S.warp_sums);  // threads >= 256 contribute 0
+        if (tid < RADIX) S.bin_start[tid] = bstart;
         __syncthreads();
 
-        // ---- scatter keys into tile-sorted order in shared memory ----
-        uint16_t pos[SORT_IPT];
+        // ---- permute the tile in place: raw order -> digit-sorted order ----
+        unsigned long long key[SORT_IPT];
+        uint32_t val[SORT_IPT];
+#pragma unroll
+        for (int it = 0; it < SORT_IPT; it++) {
+            key[it] = sk[wbase + it * 32];
+            val[it] = sv[wbase + it * 32];
+        }
+        __syncthreads();
 #pragma unroll
         for (int it = 0; it < SORT_IPT; it++) {
             const uint32_t d = (uint32_t)(key[it] >> shift) & 255u;
             const uint32_t p = S.bin_start[d] + S.whist[warp][d] + rank[it];
-            pos[it] = (uint16_t)p;
-            S.keys[p] = key[it];
+            sk[p] = key[it];
+            sv[p] = val[it];
+        }
+
+        // ---- decoupled look-back for digit `tid`, LB_WINDOW predecessors in flight ----
+        if (tid < RADIX) {
+            uint32_t excl = 0;
+            int t = (int)tile - 1;
+            bool done = tile == 0;
+            while (!done) {
+                unsigned long long w[LB_WINDOW];
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++)
+                    w[j] = (t - j >= 0) ? ld_volatile(status + (size_t)(t - j) * RADIX + tid) : (epoch_hi | LB_PREFIX);
+#pragma unroll
+                for (int j = 0; j < LB_WINDOW; j++) {
+                    if (done) break;
+                    const uint32_t lo = (uint32_t)w[j];
+                    if ((w[j] >> 32) != epoch) break;  // not yet published in this pass: poll again from here
+                    excl += lo & LB_COUNT;
+                    --t;
+                    if (lo & LB_PREFIX) done = true;
+                }
+            }
+            if (tile != 0) st_volatile(status + (size_t)tile * RADIX + tid, epoch_hi | LB_PREFIX | (excl + count));
+            S.out_base[tid] = (int32_t)(S.gexcl[tid] + excl) - (int32_t)bstart;
         }
         __syncthreads();
-        uint8_t dig[SORT_IPT];
-#pragma unroll
+
+        // ---- coalesced global scatter: consecutive idx of one digit -> consecutive addresses ----
+#pragma unroll 4
         for (int it = 0; it < SORT_IPT; it++) {
             const uint32_t idx = it * SORT_THREADS + tid;
-            const unsigned long long k = S.keys[idx];
-            const uint32_t d = (uint32_t)(k >> shift) & 255u;
-            dig[it] = (uint8_t)d;
-            if (idx < valid) kout[S.out_base[d] + (int32_t)idx] = k;
+            const unsigned long long k = sk[idx];
+            const uint32_t v = sv[idx];
+            const int32_t g = S.out_base[(uint32_t)(k >> shift) & 255u] + (int32_t)idx;
+            if (idx < valid) {
+                kout[g] = k;
+                vout[g] = v;
+            }
         }
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < SORT_IPT; it++) S.vals[pos[it]] = val[it];
-        __syncthreads();
-#pragma unroll
-        for (int it = 0; it < SORT_IPT; it++) {
-            const uint32_t idx = it * SORT_THREADS + tid;
-            if (idx < valid) vout[S.out_base[dig[it]] + (int32_t)idx] = S.vals[idx];
-        }
-        __syncthreads();
+        __syncthreads();  // buffer `cur` may now be refilled by TMA
+        cur ^= 1;
     }
 }
 
@@ -277,9 +356,12 @@ cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s) {
         if (p.events && (e = cudaEventRecord(p.events[0], s)) != cudaSuccess) return e;
     }
     const size_t smem = sizeof(PassSmem);
-    static_assert(sizeof(PassSmem) <= 48 * 1024, "PassSmem must fit the default dynamic shared memory limit");
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     uint32_t blocks = (hint + SORT_TILE - 1) / SORT_TILE;
-    const uint32_t cap = (uint32_t)p.num_sms * 4;  // ticket loop: any grid size is correct
+    const uint32_t cap = (uint32_t)p.num_sms;  // persistent: one CTA per SM; ticket loop: any grid size is correct
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     for (uint32_t pass = 0; pass < P; pass++) {

@@ -220,7 +220,8 @@ def main():
     fmt, bpp = g.FORMAT_BGRA8, 4
     band_buf = torch.zeros((rows_per * 16, W, bpp), dtype=torch.uint8, device=dev)
     full_buf = torch.zeros((world * rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) if world > 1 else band_buf
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: NULL would mean the context's own stream
+    torch.cuda.set_stream(stream)
 
     # first frame sizes the instance arena (regrow path), then keep 25% headroom for the orbit
     ctx.render_into(cams[0], band_buf.data_ptr(), fmt, rows=band, stream=stream, sync=True)
