@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 PKG_ROOT = Path(__file__).resolve().parents[2]  # .../3dgs.cpp_b200
-LIB_PATH = PKG_ROOT / "libgsb200.so"
+LIB_PATH = Path(os.environ.get("GSB200_LIB", PKG_ROOT / "libgsb200.so"))  # override only for A/B experiments
 HOST_LIB_PATH = PKG_ROOT / "libgsb200_host.so"
 
 if not LIB_PATH.exists():

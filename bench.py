@@ -243,7 +243,7 @@ def main():
         frame(i, sync=True)
 
     # per-stage / per-kernel times (library cudaEvents), sampled on separate untimed frames
-    stage_acc, m_acc, cons_acc, vis_acc = {}, [], [], []
+    stage_acc, m_acc, cons_acc, vis_acc, pass_acc = {}, [], [], [], []
     for i in range(NUM_CAMERAS):
         frame(i, sync=True)
         s = ctx.stats()
@@ -255,7 +255,9 @@ def main():
         cons_acc.append(s.blend_consumed)
         vis_acc.append(s.num_visible)
         passes = s.sort_passes
+        pass_acc.append(d["sort_pass_ms"])
     stage = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    pass_each = [float(x) for x in np.mean(np.array(pass_acc), axis=0)] if pass_acc and pass_acc[0] else []
     M, NV, CONS = float(np.mean(m_acc)), float(np.mean(vis_acc)), float(np.mean(cons_acc))
 
     # ---- value: K frames, device resident, one stream, CUDA events, max over ranks ----
@@ -329,6 +331,7 @@ def main():
             "roofline": roof,
             "kernels": kern,
             "stage_ms": stage,
+            "sort_pass_ms_each": pass_each,
             "sort_keys_per_s": M / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
             "blend_pair_evals_per_s": CONS * 256 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
         }
