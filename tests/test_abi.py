@@ -48,9 +48,11 @@ def test_no_cpu_fallback_without_device(gs):
 
 
 def test_product_never_references_the_oracle():
-    """oracle/ is test infrastructure: nothing under the package may include, link or import it."""
+    """oracle/ is test infrastructure: nothing under the package may include, link, load or import it
+    (comments that cite it for documentation are fine)."""
     pkg = ROOT / "3dgs.cpp_b200"
+    bad = re.compile(r'#\s*include\s*[<"][^>"]*oracle|liboracle|-loracle|\bimport\s+oracle\b|\bfrom\s+oracle\b|dlopen\([^)]*oracle|\.\./oracle')
     for p in pkg.rglob("*"):
-        if p.suffix in {".cu", ".cuh", ".cpp", ".h", ".py", ".txt"} or p.name in {"Makefile"}:
-            text = p.read_text(errors="ignore")
-            assert "gs_oracle" not in text and "liboracle" not in text and "import oracle" not in text, p
+        if p.suffix in {".cu", ".cuh", ".cpp", ".h", ".py", ".txt", ".cmake"} or p.name in {"Makefile", "CMakeLists.txt"}:
+            m = bad.search(p.read_text(errors="ignore"))
+            assert m is None, (p, m.group(0))
