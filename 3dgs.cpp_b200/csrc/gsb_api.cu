@@ -39,11 +39,15 @@ struct gsb_ctx {
     // frame state
     Control* ctl = nullptr;
     Control* ctl_host = nullptr;  // pinned mirror, filled at the end of each frame
-    unsigned long long* pre_status = nullptr;
+    uint32_t* project_status = nullptr;        // k_project look-back words (one per 256-Gaussian chunk)
+    unsigned long long* emit_status = nullptr;  // k_emit look-back words
     float4* recs = nullptr;
+    uint2* einfo = nullptr;
+    uint32_t* dkeys[2] = {nullptr, nullptr};  // Gaussian-level sort: depth bits
+    uint32_t* dvals[2] = {nullptr, nullptr};  //                       compact ids
     uint64_t capacity = 0;
-    unsigned long long* keys[2] = {nullptr, nullptr};
-    uint32_t* vals[2] = {nullptr, nullptr};
+    uint32_t* keys[2] = {nullptr, nullptr};   // instance-level sort: tile ids
+    uint32_t* vals[2] = {nullptr, nullptr};   //                      compact ids
     unsigned long long* sort_status = nullptr;
     uint32_t sort_status_tiles = 0;
     uint32_t epoch = 8;
@@ -55,22 +59,22 @@ struct gsb_ctx {
     int mode = GSB_MODE_EXACT;
     bool debug = false;
     bool timers = true;
-    cudaEvent_t ev[6] = {};
-    cudaEvent_t ev_sort[9] = {};  // after hist, after each pass
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_sort[9] = {};  // instance sort: after hist, after each pass
     cudaEvent_t ev_done = nullptr;
     bool frame_pending = false;
     bool have_frame = false;
     uint32_t m_hint = 0;
+    uint32_t nv_hint = 0;
     uint32_t regrow_count = 0;
 
     // description of the last frame (for stats / debug download)
-    uint32_t last_w = 0, last_h = 0, last_tiles_x = 0, last_tiles_y = 0, last_passes = 0, last_final = 0;
+    uint32_t last_w = 0, last_h = 0, last_tiles_x = 0, last_tiles_y = 0, last_passes = 0, last_depth_passes = 0, last_final = 0;
 
     // debug copies
     uint32_t* dbg_tiles = nullptr;
-    uint32_t* dbg_scan = nullptr;
     uint4* dbg_aabb = nullptr;
-    unsigned long long* dbg_keys_unsorted = nullptr;
+    uint32_t* dbg_keys_unsorted = nullptr;
     uint32_t* dbg_vals_unsorted = nullptr;
     uint64_t dbg_m = 0;
 };
@@ -115,18 +119,31 @@ int free_arena(gsb_ctx* ctx) {
     return GSB_OK;
 }
 
+int ensure_sort_status(gsb_ctx* ctx, uint64_t items) {
+    const uint32_t tiles = (uint32_t)((items + sort_tile_items() - 1) / sort_tile_items());
+    if (tiles <= ctx->sort_status_tiles) return GSB_OK;
+    dev_free(ctx->sort_status);
+    ctx->sort_status_tiles = 0;
+    CK(dev_alloc(&ctx->sort_status, (size_t)tiles * 256));
+    CK(cudaMemset(ctx->sort_status, 0, (size_t)tiles * 256 * sizeof(unsigned long long)));
+    ctx->sort_status_tiles = tiles;
+    return GSB_OK;
+}
+
 int ensure_arena(gsb_ctx* ctx, uint64_t capacity) {
     if (capacity <= ctx->capacity) return GSB_OK;
     if (capacity >= (1ull << 30)) return fail(ctx, GSB_ERR_OVERFLOW, "instance arena limited to 2^30 - 1 entries");
-    free_arena(ctx);
+    dev_free(ctx->keys[0]);
+    dev_free(ctx->keys[1]);
+    dev_free(ctx->vals[0]);
+    dev_free(ctx->vals[1]);
+    ctx->capacity = 0;
     CK(dev_alloc(&ctx->keys[0], capacity));
     CK(dev_alloc(&ctx->keys[1], capacity));
     CK(dev_alloc(&ctx->vals[0], capacity));
     CK(dev_alloc(&ctx->vals[1], capacity));
-    const uint32_t tiles = (uint32_t)((capacity + sort_tile_items() - 1) / sort_tile_items());
-    CK(dev_alloc(&ctx->sort_status, (size_t)tiles * 256));
-    CK(cudaMemset(ctx->sort_status, 0, (size_t)tiles * 256 * sizeof(unsigned long long)));
-    ctx->sort_status_tiles = tiles;
+    int rc = ensure_sort_status(ctx, std::max<uint64_t>(capacity, ctx->n));
+    if (rc != GSB_OK) return rc;
     ctx->capacity = capacity;
     return GSB_OK;
 }
@@ -144,6 +161,7 @@ int wait_frame(gsb_ctx* ctx) {
         CK(cudaEventSynchronize(ctx->ev_done));
         ctx->frame_pending = false;
         ctx->m_hint = ctx->ctl_host->num_instances;
+        ctx->nv_hint = ctx->ctl_host->num_visible;
     }
     return GSB_OK;
 }
@@ -163,10 +181,16 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     const uint32_t chunks = (n + 255) / 256;
 
     CK(cudaMemsetAsync(ctx->ctl, 0, sizeof(Control), stream));
-    CK(cudaMemsetAsync(ctx->pre_status, 0, (size_t)std::max(chunks, 1u) * sizeof(unsigned long long), stream));
+    CK(cudaMemsetAsync(ctx->project_status, 0, (size_t)std::max(chunks, 1u) * sizeof(uint32_t), stream));
+    CK(cudaMemsetAsync(ctx->emit_status, 0, (size_t)std::max(chunks, 1u) * sizeof(unsigned long long), stream));
+    if (ctx->epoch >= 0xffffff00u) {  // epoch wrap: clear the look-back tags once
+        CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
+        ctx->epoch = 8;
+    }
     if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
 
-    PreprocessParams pp{};
+    // ---- k_project: preprocess.comp + survivor compaction ----
+    ProjectParams pp{};
     pp.pos_op = ctx->pos_op;
     pp.cov_a = ctx->cov_a;
     pp.cov_b = ctx->cov_b;
@@ -176,18 +200,53 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     pp.tile_row_begin = rb;
     pp.tile_row_end = re;
     pp.recs = ctx->recs;
-    pp.keys = ctx->keys[0];
-    pp.vals = ctx->vals[0];
-    pp.capacity = (uint32_t)ctx->capacity;
-    pp.status = ctx->pre_status;
+    pp.einfo = ctx->einfo;
+    pp.dkeys = ctx->dkeys[0];
+    pp.dvals = ctx->dvals[0];
+    pp.status = ctx->project_status;
     pp.ctl = ctx->ctl;
     pp.dbg_tiles = ctx->dbg_tiles;
-    pp.dbg_scan = ctx->dbg_scan;
     pp.dbg_aabb = ctx->dbg_aabb;
-    CK(launch_preprocess(pp, ctx->debug, stream));
+    CK(launch_project(pp, ctx->debug, stream));
     if (ctx->timers) CK(cudaEventRecord(ctx->ev[1], stream));
 
-    if (ctx->debug) {  // keep the unsorted keys (sortK/VBufferEven right after preprocess_sort)
+    // ---- Gaussian-level Onesweep: the 32 depth bits (the reference's passes 0-3), N_v elements ----
+    SortParams sa{};
+    sa.keys[0] = ctx->dkeys[0];
+    sa.keys[1] = ctx->dkeys[1];
+    sa.vals[0] = ctx->dvals[0];
+    sa.vals[1] = ctx->dvals[1];
+    sa.key_bytes = 4;
+    sa.d_m = &ctx->ctl->num_visible;
+    sa.m_hint = ctx->nv_hint ? ctx->nv_hint : n;
+    sa.key_bits = 32;
+    sa.status = ctx->sort_status;
+    sa.status_tiles = ctx->sort_status_tiles;
+    sa.epoch_base = ctx->epoch;
+    sa.sc = &ctx->ctl->sort_depth;
+    sa.num_sms = ctx->num_sms;
+    sa.events = nullptr;
+    uint32_t depth_passes = 0;
+    CK(launch_sort(sa, &depth_passes, stream));
+    const int fin_a = depth_passes & 1;
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[2], stream));
+
+    // ---- k_emit: scan of tile counts + (tile id, payload) emission in depth order ----
+    EmitParams ep{};
+    ep.sorted_cid = ctx->dvals[fin_a];
+    ep.einfo = ctx->einfo;
+    ep.nv_hint = sa.m_hint;
+    ep.tiles_x = tiles_x;
+    ep.keys = ctx->keys[0];
+    ep.vals = ctx->vals[0];
+    ep.capacity = (uint32_t)ctx->capacity;
+    ep.status = ctx->emit_status;
+    ep.ctl = ctx->ctl;
+    ep.num_sms = ctx->num_sms;
+    CK(launch_emit(ep, stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[3], stream));
+
+    if (ctx->debug) {  // keep the emitted (not yet tile-sorted) pairs: the reference's sort buffers after its pass 3
         CK(cudaStreamSynchronize(stream));
         uint32_t m = 0;
         CK(cudaMemcpy(&m, &ctx->ctl->num_instances, sizeof m, cudaMemcpyDeviceToHost));
@@ -195,37 +254,35 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
         dev_free(ctx->dbg_vals_unsorted);
         CK(dev_alloc(&ctx->dbg_keys_unsorted, m));
         CK(dev_alloc(&ctx->dbg_vals_unsorted, m));
-        CK(cudaMemcpyAsync(ctx->dbg_keys_unsorted, ctx->keys[0], (size_t)m * 8, cudaMemcpyDeviceToDevice, stream));
+        CK(cudaMemcpyAsync(ctx->dbg_keys_unsorted, ctx->keys[0], (size_t)m * 4, cudaMemcpyDeviceToDevice, stream));
         CK(cudaMemcpyAsync(ctx->dbg_vals_unsorted, ctx->vals[0], (size_t)m * 4, cudaMemcpyDeviceToDevice, stream));
         ctx->dbg_m = m;
     }
 
+    // ---- instance-level Onesweep: the tile-id bits (the reference's passes 4-7), M elements ----
     SortParams sp{};
     sp.keys[0] = ctx->keys[0];
     sp.keys[1] = ctx->keys[1];
     sp.vals[0] = ctx->vals[0];
     sp.vals[1] = ctx->vals[1];
+    sp.key_bytes = 4;
     sp.d_m = &ctx->ctl->num_instances;
     sp.m_hint = ctx->m_hint ? ctx->m_hint : (uint32_t)std::min<uint64_t>(ctx->capacity, 4u * 1024 * 1024);
-    sp.key_bits = 32 + bits_for(T);
+    sp.key_bits = bits_for(T);
     sp.status = ctx->sort_status;
     sp.status_tiles = ctx->sort_status_tiles;
-    sp.epoch_base = ctx->epoch;
+    sp.epoch_base = ctx->epoch + 4;
     ctx->epoch += 8;
-    if (ctx->epoch >= 0xfffffff0u) {  // epoch wrap: clear the tags once
-        CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
-        ctx->epoch = 8;
-    }
-    sp.ctl = ctx->ctl;
+    sp.sc = &ctx->ctl->sort_tile;
     sp.num_sms = ctx->num_sms;
     sp.events = ctx->timers ? ctx->ev_sort : nullptr;
     uint32_t passes = 0;
     CK(launch_sort(sp, &passes, stream));
     const int fin = passes & 1;
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[2], stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[4], stream));
 
     CK(launch_tile_ranges(ctx->keys[fin], sp.d_m, sp.m_hint, ctx->ranges, T, ctx->num_sms, stream));
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[3], stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[5], stream));
 
     BlendParams bp{};
     bp.recs = ctx->recs;
@@ -242,9 +299,9 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     bp.mode = ctx->mode;
     bp.ctl = ctx->ctl;
     CK(launch_blend(bp, stream));
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[4], stream));
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[6], stream));
 
-    CK(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, offsetof(Control, hist), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, offsetof(Control, sort_depth), cudaMemcpyDeviceToHost, stream));
     CK(cudaEventRecord(ctx->ev_done, stream));
     ctx->frame_pending = true;
     ctx->have_frame = true;
@@ -253,6 +310,7 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     ctx->last_tiles_x = tiles_x;
     ctx->last_tiles_y = tiles_y;
     ctx->last_passes = passes;
+    ctx->last_depth_passes = depth_passes;
     ctx->last_final = (uint32_t)fin;
     return GSB_OK;
 }
@@ -343,13 +401,18 @@ void gsb_destroy(gsb_ctx* ctx) {
     dev_free(ctx->sh);
     dev_free(ctx->ctl);
     if (ctx->ctl_host) cudaFreeHost(ctx->ctl_host);
-    dev_free(ctx->pre_status);
+    dev_free(ctx->project_status);
+    dev_free(ctx->emit_status);
     dev_free(ctx->recs);
+    dev_free(ctx->einfo);
+    dev_free(ctx->dkeys[0]);
+    dev_free(ctx->dkeys[1]);
+    dev_free(ctx->dvals[0]);
+    dev_free(ctx->dvals[1]);
     free_arena(ctx);
     dev_free(ctx->ranges);
     if (ctx->fb) cudaFree(ctx->fb);
     dev_free(ctx->dbg_tiles);
-    dev_free(ctx->dbg_scan);
     dev_free(ctx->dbg_aabb);
     dev_free(ctx->dbg_keys_unsorted);
     dev_free(ctx->dbg_vals_unsorted);
@@ -375,9 +438,14 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     dev_free(ctx->cov_b);
     dev_free(ctx->sh);
     dev_free(ctx->recs);
-    dev_free(ctx->pre_status);
+    dev_free(ctx->einfo);
+    dev_free(ctx->dkeys[0]);
+    dev_free(ctx->dkeys[1]);
+    dev_free(ctx->dvals[0]);
+    dev_free(ctx->dvals[1]);
+    dev_free(ctx->project_status);
+    dev_free(ctx->emit_status);
     dev_free(ctx->dbg_tiles);
-    dev_free(ctx->dbg_scan);
     dev_free(ctx->dbg_aabb);
     ctx->n = 0;
     CK(dev_alloc(&ctx->pos_op, n));
@@ -385,10 +453,15 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     CK(dev_alloc(&ctx->cov_b, n));
     CK(dev_alloc(&ctx->sh, n * 48));
     CK(dev_alloc(&ctx->recs, n * 3));
-    CK(dev_alloc(&ctx->pre_status, (n + 255) / 256));
+    CK(dev_alloc(&ctx->einfo, n));
+    CK(dev_alloc(&ctx->dkeys[0], n));
+    CK(dev_alloc(&ctx->dkeys[1], n));
+    CK(dev_alloc(&ctx->dvals[0], n));
+    CK(dev_alloc(&ctx->dvals[1], n));
+    CK(dev_alloc(&ctx->project_status, (n + 255) / 256));
+    CK(dev_alloc(&ctx->emit_status, (n + 255) / 256));
     if (ctx->debug) {
         CK(dev_alloc(&ctx->dbg_tiles, n));
-        CK(dev_alloc(&ctx->dbg_scan, n));
         CK(dev_alloc(&ctx->dbg_aabb, n));
     }
     // stream the AoS records through a bounded staging buffer (C5: 50 M x 240 B = 12 GB on the host)
@@ -418,6 +491,11 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     if (staging) cudaFree(staging);
     ctx->n = n;
     ctx->m_hint = 0;
+    ctx->nv_hint = 0;
+    {
+        int rc = ensure_sort_status(ctx, std::max<uint64_t>(n, ctx->capacity));
+        if (rc != GSB_OK) return rc;
+    }
     // the reference starts the sort arena at N entries (sortBufferSizeMultiplier = 1, Renderer.cpp:235-242)
     if (ctx->capacity == 0) {
         int rc = ensure_arena(ctx, std::max<uint64_t>(n, 1024));
@@ -440,7 +518,6 @@ int gsb_set_debug(gsb_ctx* ctx, int debug) {
     ctx->debug = debug != 0;
     if (ctx->debug && ctx->n && !ctx->dbg_tiles) {
         CK(dev_alloc(&ctx->dbg_tiles, ctx->n));
-        CK(dev_alloc(&ctx->dbg_scan, ctx->n));
         CK(dev_alloc(&ctx->dbg_aabb, ctx->n));
     }
     return GSB_OK;
@@ -535,26 +612,32 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
     out->blend_consumed = c->blend_consumed;
     out->instance_capacity = ctx->capacity;
     out->sort_passes = ctx->last_passes;
+    out->sort_depth_passes = ctx->last_depth_passes;
     out->regrow_count = ctx->regrow_count;
     if (ctx->timers) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
-        out->preprocess_ms = ms;  // fused preprocess + scan + key emission
+        out->preprocess_ms = ms;  // k_project
         CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
-        out->sort_ms = ms;
+        out->sort_depth_ms = ms;  // Gaussian-level Onesweep (histogram + 4 passes over N_v)
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        out->preprocess_sort_ms = ms;  // k_emit (scan + key emission); prefix_sum_ms stays 0: fused here
+        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+        out->sort_tile_ms = ms;  // instance-level Onesweep
+        out->sort_ms = out->sort_depth_ms + out->sort_tile_ms;
         if (ctx->last_passes) {
-            CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev_sort[0]));
+            CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev_sort[0]));
             out->sort_hist_ms = ms;
             for (uint32_t p = 0; p < ctx->last_passes && p < 8; p++) {
                 CK(cudaEventElapsedTime(&ms, ctx->ev_sort[p], ctx->ev_sort[p + 1]));
                 out->sort_pass_ms[p] = ms;
             }
         }
-        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
         out->tile_boundary_ms = ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
         out->render_ms = ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]));
         out->frame_ms = ms;
     }
     if (c->overflow) return fail(ctx, GSB_ERR_OVERFLOW, "last frame overflowed the instance arena (gsb_render regrows; gsb_render_async does not)");
@@ -592,13 +675,6 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
     const uint64_t n = ctx->n;
     const uint32_t nv = ctx->have_frame ? ctx->ctl_host->num_visible : 0;
     const uint64_t m = ctx->have_frame ? ctx->ctl_host->num_instances : 0;
-    auto orig_ids = [&](std::vector<uint32_t>& ids) -> int {  // compact id -> original Gaussian index
-        std::vector<float4> recs((size_t)nv * 3);
-        if (nv) CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
-        ids.resize(nv);
-        for (uint32_t c = 0; c < nv; c++) memcpy(&ids[c], &recs[(size_t)c * 3 + 2].w, 4);
-        return GSB_OK;
-    };
     switch (which) {
         case GSB_BUF_COV3D: {
             std::vector<float4> a(n);
@@ -653,26 +729,40 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
         case GSB_BUF_TILES_OVERLAP:
             if (n) CK(cudaMemcpy(dst, ctx->dbg_tiles, n * 4, cudaMemcpyDeviceToHost));
             return GSB_OK;
-        case GSB_BUF_PREFIX_SUM:
-            if (n) CK(cudaMemcpy(dst, ctx->dbg_scan, n * 4, cudaMemcpyDeviceToHost));
+        case GSB_BUF_PREFIX_SUM: {  // derived on the host: the device scans in depth order inside k_emit
+            uint32_t* o = static_cast<uint32_t*>(dst);
+            if (n) CK(cudaMemcpy(o, ctx->dbg_tiles, n * 4, cudaMemcpyDeviceToHost));
+            uint32_t run = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                run += o[i];
+                o[i] = run;
+            }
             return GSB_OK;
+        }
         case GSB_BUF_KEYS_UNSORTED:
-            if (m) CK(cudaMemcpy(dst, ctx->dbg_keys_unsorted, m * 8, cudaMemcpyDeviceToHost));
-            return GSB_OK;
         case GSB_BUF_KEYS_SORTED:
-            if (m) CK(cudaMemcpy(dst, ctx->keys[ctx->last_final], m * 8, cudaMemcpyDeviceToHost));
-            return GSB_OK;
         case GSB_BUF_VALS_UNSORTED:
         case GSB_BUF_VALS_SORTED: {
-            std::vector<uint32_t> ids;
-            int rc = orig_ids(ids);
-            if (rc != GSB_OK) return rc;
-            uint32_t* o = static_cast<uint32_t*>(dst);
-            const uint32_t* src = which == GSB_BUF_VALS_UNSORTED ? ctx->dbg_vals_unsorted : ctx->vals[ctx->last_final];
-            if (m) CK(cudaMemcpy(o, src, m * 4, cudaMemcpyDeviceToHost));
+            // device pairs are (u32 tile id, u32 compact id); rebuild the reference's (tile << 32 | depth, Gaussian index)
+            const bool sorted = which == GSB_BUF_KEYS_SORTED || which == GSB_BUF_VALS_SORTED;
+            const bool want_keys = which == GSB_BUF_KEYS_UNSORTED || which == GSB_BUF_KEYS_SORTED;
+            std::vector<float4> recs((size_t)nv * 3);
+            if (nv) CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+            std::vector<uint32_t> tk(m), cv(m);
+            const uint32_t* ksrc = sorted ? ctx->keys[ctx->last_final] : ctx->dbg_keys_unsorted;
+            const uint32_t* vsrc = sorted ? ctx->vals[ctx->last_final] : ctx->dbg_vals_unsorted;
+            if (m) {
+                CK(cudaMemcpy(tk.data(), ksrc, m * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(cv.data(), vsrc, m * 4, cudaMemcpyDeviceToHost));
+            }
             for (uint64_t k = 0; k < m; k++) {
-                if (o[k] >= nv) return fail(ctx, GSB_ERR_CUDA, "corrupt payload");
-                o[k] = ids[o[k]];
+                if (cv[k] >= nv) return fail(ctx, GSB_ERR_CUDA, "corrupt payload");
+                const float4 r2 = recs[(size_t)cv[k] * 3 + 2];
+                uint32_t depth_bits, orig;
+                memcpy(&depth_bits, &r2.y, 4);
+                memcpy(&orig, &r2.w, 4);
+                if (want_keys) static_cast<uint64_t*>(dst)[k] = ((uint64_t)tk[k] << 32) | depth_bits;
+                else static_cast<uint32_t*>(dst)[k] = orig;
             }
             return GSB_OK;
         }
@@ -702,8 +792,9 @@ int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
     const uint32_t m32 = (uint32_t)m;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->ctl->num_instances, &m32, 4, cudaMemcpyHostToDevice, s);
     SortParams sp{};
-    sp.keys[0] = reinterpret_cast<unsigned long long*>(keys);
-    sp.keys[1] = reinterpret_cast<unsigned long long*>(keys_tmp);
+    sp.keys[0] = keys;
+    sp.keys[1] = keys_tmp;
+    sp.key_bytes = 8;
     sp.vals[0] = vals;
     sp.vals[1] = vals_tmp;
     sp.d_m = &ctx->ctl->num_instances;
@@ -712,7 +803,7 @@ int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
     sp.status = status;
     sp.status_tiles = tiles;
     sp.epoch_base = 8;
-    sp.ctl = ctx->ctl;
+    sp.sc = &ctx->ctl->sort_tile;
     sp.num_sms = ctx->num_sms;
     sp.events = nullptr;
     uint32_t passes = 0;

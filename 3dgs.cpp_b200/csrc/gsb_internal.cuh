@@ -9,7 +9,9 @@
 //               r0 = (uv.x, uv.y, conic.x, conic.y)
 //               r1 = (conic.z, opacity, color.r, color.g)
 //               r2 = (color.b, depth, radius, bits(original index))
-//           keys[2][cap] u64 = (tile << 32 | bits(depth)), vals[2][cap] u32 = compact id
+//           einfo[Nv]  uint2 (x0 | y0 << 16, w | h << 16) tile AABB of the survivor
+//           dkeys[2][Nv] u32 bits(depth), dvals[2][Nv] u32 compact id      -- Gaussian-level sort
+//           keys[2][cap] u32 tile id,     vals[2][cap] u32 compact id      -- instance-level sort
 //           ranges[T] uint2 (start, end) per tile
 #pragma once
 #include <cuda_runtime.h>
@@ -23,21 +25,27 @@
 
 namespace gsb {
 
+// control words of one Onesweep sort (device memory, zeroed at frame start)
+struct SortCtl {
+    uint32_t ticket[8];     // tile tickets, one per radix pass
+    uint32_t hist[8][256];  // global digit histograms
+};
+
 // ---- per-frame control block (device memory, zeroed by one memset at frame start) ----
 struct Control {
-    uint32_t pre_ticket;       // chunk tickets of k_preprocess
-    uint32_t sort_ticket[8];   // tile tickets, one per radix pass
-    uint32_t ranges_ticket;
+    uint32_t project_ticket;   // chunk tickets of k_project
+    uint32_t emit_ticket;      // chunk tickets of k_emit
     uint32_t num_visible;      // N_v
     uint32_t num_instances;    // M clamped to the arena capacity
     uint32_t overflow;         // 1 if M_total > capacity
-    uint32_t pad0;
+    uint32_t pad0[3];
     unsigned long long instances_total;  // unclamped M
     unsigned long long blend_consumed;
-    uint32_t hist[8][256];     // global digit histograms of the Onesweep sort
+    SortCtl sort_depth;        // Gaussian-level sort (32-bit depth keys)
+    SortCtl sort_tile;         // instance-level sort (tile-id keys); also used by gsb_sort_pairs
 };
 
-struct PreprocessParams {
+struct ProjectParams {
     const float4* pos_op;
     const float4* cov_a;
     const float2* cov_b;
@@ -45,33 +53,47 @@ struct PreprocessParams {
     uint32_t n;
     gsb_uniforms ubo;
     uint32_t tile_row_begin, tile_row_end;  // band clip (multi-GPU); [0, tiles_y) = whole frame
-    // outputs
+    // outputs (compacted by survivor rank)
     float4* recs;
-    unsigned long long* keys;
-    uint32_t* vals;
-    uint32_t capacity;
-    unsigned long long* status;  // decoupled look-back words, one per 256-Gaussian chunk
+    uint2* einfo;
+    uint32_t* dkeys;
+    uint32_t* dvals;
+    uint32_t* status;  // decoupled look-back words, one per 256-Gaussian chunk
     Control* ctl;
     // debug outputs (may be null)
     uint32_t* dbg_tiles;  // N
-    uint32_t* dbg_scan;   // N inclusive
     uint4* dbg_aabb;      // N
+};
+
+struct EmitParams {
+    const uint32_t* sorted_cid;  // survivors in (depth, index) order
+    const uint2* einfo;
+    uint32_t nv_hint;            // host estimate of N_v (sizes the grid only)
+    uint32_t tiles_x;
+    uint32_t* keys;              // tile ids
+    uint32_t* vals;              // compact ids
+    uint32_t capacity;
+    unsigned long long* status;  // decoupled look-back words, one per 256-survivor chunk
+    Control* ctl;
+    int num_sms;
 };
 
 cudaError_t launch_cov3d(const float* vtx_aos, uint64_t count, uint64_t dst_offset, float4* pos_op,
                          float4* cov_a, float2* cov_b, float* sh, float scale_factor, cudaStream_t s);
-cudaError_t launch_preprocess(const PreprocessParams& p, bool debug, cudaStream_t s);
+cudaError_t launch_project(const ProjectParams& p, bool debug, cudaStream_t s);
+cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);
 
 struct SortParams {
-    unsigned long long* keys[2];
+    void* keys[2];             // u32 or u64 keys (key_bytes)
     uint32_t* vals[2];
-    const uint32_t* d_m;       // device pointer to M
-    uint32_t m_hint;           // host estimate of M (sizes the grids only; any value is correct)
+    int key_bytes;             // 4 or 8
+    const uint32_t* d_m;       // device pointer to the element count
+    uint32_t m_hint;           // host estimate of the count (sizes the grids only; any value is correct)
     uint32_t key_bits;
     unsigned long long* status;  // epoch-tagged look-back words [tiles][256]
     uint32_t status_tiles;     // capacity of status in tiles
     uint32_t epoch_base;       // unique per sort call; pass p uses epoch_base + p
-    Control* ctl;              // uses ctl->hist and ctl->sort_ticket (must be zero on entry)
+    SortCtl* sc;               // must be zero on entry
     int num_sms;
     cudaEvent_t* events;       // optional: events[0] after the histogram, events[1 + p] after pass p
 };
@@ -79,8 +101,8 @@ struct SortParams {
 cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s);
 uint32_t sort_tile_items();
 
-cudaError_t launch_tile_ranges(const unsigned long long* keys, const uint32_t* d_m, uint32_t m_hint,
-                               uint2* ranges, uint32_t num_tiles, int num_sms, cudaStream_t s);
+cudaError_t launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_m, uint32_t m_hint, uint2* ranges,
+                               uint32_t num_tiles, int num_sms, cudaStream_t s);
 
 struct BlendParams {
     const float4* recs;

@@ -1,17 +1,19 @@
-// gsb_preprocess.cu -- ONE kernel for the reference's first three stages:
-//   preprocess.comp:115-182   (project, cull, EWA cov2d, conic, radius, tile AABB, degree-3 SH colour)
-//   prefix_sum.comp:32-58 x (log2 N + 1) dispatches (Renderer.cpp:497-526)  -> single-pass decoupled look-back scan
-//   preprocess_sort.comp:31-60 (emit (tile<<32 | depth) keys + payload at the scan offset)
-// and it removes the mid-frame fence + host read of M (Renderer.cpp:391,538): M stays in HBM.
+// gsb_preprocess.cu -- the reference's first three stages, re-cut for a two-level LSD sort.
 //
-// B200 mapping: 256 Gaussians per CTA, one per thread; coalesced LDG.128 of the SoA position /
-// covariance arrays; the 192-B SH record is fetched by cull survivors only; survivors are compacted
-// (dense 48-B blend records => dense, L2-friendly gathers in the blend); key emission is a
-// block-cooperative expansion so every 8-B key / 4-B payload store is coalesced, in exactly the
-// reference's order (Gaussian-major, x-outer, y-inner).
+//   k_project  = preprocess.comp:115-182 (project, cull, EWA cov2d, conic, radius, tile AABB,
+//                degree-3 SH colour) + stream compaction of the cull survivors (single-pass
+//                decoupled look-back scan).  Per survivor it writes the 48-B blend record, the
+//                tile AABB and the 32-bit depth key of the Gaussian-level sort.
+//   k_emit     = prefix_sum.comp:32-58 (x (log2 N + 1) dispatches, Renderer.cpp:497-526) +
+//                preprocess_sort.comp:31-60: one single-pass decoupled look-back scan of the tile
+//                counts and the emission of one (tile id, payload) pair per covered tile -- but
+//                over the survivors in DEPTH order (after the Gaussian-level sort), so the low 32
+//                key bits of the reference's 64-bit (tile << 32 | depth) key are already in order
+//                and only the tile id is left to sort at instance granularity.
+// Both remove the mid-frame fence + host read of M (Renderer.cpp:391,538): counts stay in HBM.
 //
 // Arithmetic: compiled with -fmad=false; every fp32 operation is a single IEEE op in the order
-// of the GLSL source, so results are value-identical to oracle/gs_oracle.c (bit-exact parity).
+// of the GLSL source, so results are value-identical to the oracle (bit-exact parity).
 #include "gsb_internal.cuh"
 
 namespace gsb {
@@ -21,20 +23,18 @@ namespace {
 constexpr int PRE_THREADS = 256;
 constexpr unsigned FULL = 0xffffffffu;
 
-// look-back status word: [63:62] flag, [61:32] survivors, [31:0] tile instances (saturating)
-constexpr unsigned long long ST_AGG = 1ull << 62;
-constexpr unsigned long long ST_PREFIX = 2ull << 62;
-constexpr unsigned long long ST_FLAGS = 3ull << 62;
+// k_project look-back word: [31:30] flag, [29:0] survivors
+constexpr uint32_t S1_AGG = 1u << 30, S1_PREFIX = 2u << 30, S1_FLAGS = 3u << 30, S1_COUNT = (1u << 30) - 1u;
+// k_emit look-back word: [63:62] flag, [61:0] instances
+constexpr unsigned long long S2_AGG = 1ull << 62, S2_PREFIX = 2ull << 62, S2_FLAGS = 3ull << 62, S2_COUNT = (1ull << 62) - 1ull;
 
-__device__ __forceinline__ unsigned long long st_pack(unsigned long long flag, uint32_t surv, unsigned long long tiles) {
-    if (tiles > 0xffffffffull) tiles = 0xffffffffull;
-    return flag | ((unsigned long long)surv << 32) | tiles;
+template <typename T>
+__device__ __forceinline__ T ld_vol(const T* p) {
+    return *reinterpret_cast<const volatile T*>(p);
 }
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
-    return *reinterpret_cast<const volatile unsigned long long*>(p);
-}
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
-    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+template <typename T>
+__device__ __forceinline__ void st_vol(T* p, T v) {
+    *reinterpret_cast<volatile T*>(p) = v;
 }
 
 // common.glsl:16-33
@@ -50,67 +50,85 @@ __device__ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+struct ShDir {
+    float x, y, z, w6, w8, w9, w11, w12, w15;
+};
+
+// one term of preprocess.comp:80-98, in the shader's association order
+template <int K>
+__device__ __forceinline__ float sh_term(float a, float s, const ShDir& d) {
+    if constexpr (K == 0) return SH_C0 * s;
+    else if constexpr (K == 1) return a - (SH_C1 * s) * d.y;
+    else if constexpr (K == 2) return a + (SH_C1 * s) * d.z;
+    else if constexpr (K == 3) return a - (SH_C1 * s) * d.x;
+    else if constexpr (K == 4) return a + ((SH_C2_0 * s) * d.x) * d.y;
+    else if constexpr (K == 5) return a + ((SH_C2_1 * s) * d.y) * d.z;
+    else if constexpr (K == 6) return a + (SH_C2_2 * s) * d.w6;
+    else if constexpr (K == 7) return a + ((SH_C2_3 * s) * d.z) * d.x;
+    else if constexpr (K == 8) return a + (SH_C2_4 * s) * d.w8;
+    else if constexpr (K == 9) return a + ((SH_C3_0 * s) * d.w9) * d.y;
+    else if constexpr (K == 10) return a + (((SH_C3_1 * s) * d.x) * d.y) * d.z;
+    else if constexpr (K == 11) return a + ((SH_C3_2 * s) * d.w11) * d.y;
+    else if constexpr (K == 12) return a + ((SH_C3_3 * s) * d.z) * d.w12;
+    else if constexpr (K == 13) return a + ((SH_C3_4 * s) * d.x) * d.w11;
+    else if constexpr (K == 14) return a + ((SH_C3_5 * s) * d.w8) * d.z;
+    else return a + ((SH_C3_6 * s) * d.x) * d.w15;
+}
+
+template <int G>
+__device__ __forceinline__ void sh_group(const float4* __restrict__ sh4, float (&c)[3], const ShDir& d) {
+    // coefficients 4G .. 4G+3 = floats 12G .. 12G+11 = three float4
+    const float4 t0 = __ldg(sh4 + 3 * G), t1 = __ldg(sh4 + 3 * G + 1), t2 = __ldg(sh4 + 3 * G + 2);
+    const float f[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+        c[ch] = sh_term<4 * G + 0>(c[ch], f[0 + ch], d);
+        c[ch] = sh_term<4 * G + 1>(c[ch], f[3 + ch], d);
+        c[ch] = sh_term<4 * G + 2>(c[ch], f[6 + ch], d);
+        c[ch] = sh_term<4 * G + 3>(c[ch], f[9 + ch], d);
+    }
+}
+
 // preprocess.comp:73-108 compute_sh(); sh = 48 floats RGB-interleaved, as 12 float4.
 __device__ __forceinline__ void compute_sh(const float4* __restrict__ sh4, float px, float py, float pz,
                                            const float* cam, float& r, float& g, float& b) {
-    float f[48];
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-        const float4 t = __ldg(sh4 + k);
-        f[4 * k + 0] = t.x;
-        f[4 * k + 1] = t.y;
-        f[4 * k + 2] = t.z;
-        f[4 * k + 3] = t.w;
-    }
     const float dx = px - cam[0], dy = py - cam[1], dz = pz - cam[2];
     const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
-    const float x = dx / len, y = dy / len, z = dz / len;
-    const float xx = x * x, yy = y * y;
-    const float w6 = ((2.0f * z) * z - xx) - yy;
-    const float w8 = xx - yy;
-    const float w9 = (3.0f * x) * x - yy;
-    const float w11 = ((4.0f * z) * z - xx) - yy;
-    const float w12 = ((2.0f * z) * z - (3.0f * x) * x) - (3.0f * y) * y;
-    const float w15 = xx - (3.0f * y) * y;
-    float c[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-#define SH(k) f[(k) * 3 + ch]
-        float a = SH_C0 * SH(0);
-        a = a - (SH_C1 * SH(1)) * y;
-        a = a + (SH_C1 * SH(2)) * z;
-        a = a - (SH_C1 * SH(3)) * x;
-        a = a + ((SH_C2_0 * SH(4)) * x) * y;
-        a = a + ((SH_C2_1 * SH(5)) * y) * z;
-        a = a + (SH_C2_2 * SH(6)) * w6;
-        a = a + ((SH_C2_3 * SH(7)) * z) * x;
-        a = a + (SH_C2_4 * SH(8)) * w8;
-        a = a + ((SH_C3_0 * SH(9)) * w9) * y;
-        a = a + (((SH_C3_1 * SH(10)) * x) * y) * z;
-        a = a + ((SH_C3_2 * SH(11)) * w11) * y;
-        a = a + ((SH_C3_3 * SH(12)) * z) * w12;
-        a = a + ((SH_C3_4 * SH(13)) * x) * w11;
-        a = a + ((SH_C3_5 * SH(14)) * w8) * z;
-        a = a + ((SH_C3_6 * SH(15)) * x) * w15;
-        c[ch] = a + 0.5f;
-#undef SH
-    }
+    ShDir d;
+    d.x = dx / len;
+    d.y = dy / len;
+    d.z = dz / len;
+    const float xx = d.x * d.x, yy = d.y * d.y;
+    d.w6 = ((2.0f * d.z) * d.z - xx) - yy;
+    d.w8 = xx - yy;
+    d.w9 = (3.0f * d.x) * d.x - yy;
+    d.w11 = ((4.0f * d.z) * d.z - xx) - yy;
+    d.w12 = ((2.0f * d.z) * d.z - (3.0f * d.x) * d.x) - (3.0f * d.y) * d.y;
+    d.w15 = xx - (3.0f * d.y) * d.y;
+    float c[3] = {0.f, 0.f, 0.f};
+    sh_group<0>(sh4, c, d);
+    sh_group<1>(sh4, c, d);
+    sh_group<2>(sh4, c, d);
+    sh_group<3>(sh4, c, d);
+    c[0] = c[0] + 0.5f;
+    c[1] = c[1] + 0.5f;
+    c[2] = c[2] + 0.5f;
     r = c[0] < 0.0f ? 0.0f : c[0];  // :102-104 only the red channel is clamped
     g = c[1];
     b = c[2];
 }
 
+// ------------------------------------------------------------------------------------------
+// k_project
+// ------------------------------------------------------------------------------------------
 template <bool DEBUG>
-__global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const __grid_constant__ PreprocessParams P) {
+__global__ void __launch_bounds__(PRE_THREADS) k_project(const __grid_constant__ ProjectParams P) {
     __shared__ uint32_t s_chunk;
-    __shared__ uint32_t s_wsurv[PRE_THREADS / 32], s_wnt[PRE_THREADS / 32];
+    __shared__ uint32_t s_wsurv[PRE_THREADS / 32];
     __shared__ uint32_t s_base_surv;
-    __shared__ unsigned long long s_base_tiles;
-    __shared__ uint32_t s_off[PRE_THREADS + 1];
-    __shared__ uint4 s_info[PRE_THREADS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_chunk = atomicAdd(&P.ctl->pre_ticket, 1u);
+    if (tid == 0) s_chunk = atomicAdd(&P.ctl->project_ticket, 1u);
     __syncthreads();
     const uint32_t chunk = s_chunk;
     const uint32_t num_chunks = (P.n + PRE_THREADS - 1) / PRE_THREADS;
@@ -206,134 +224,203 @@ __global__ void __launch_bounds__(PRE_THREADS) k_preprocess(const __grid_constan
         }
     }
 
-    // ---- block scan of (survivor, tiles) ----
+    // ---- block scan of the survivor flags ----
     const unsigned surv_mask = __ballot_sync(FULL, surv);
     const uint32_t surv_rank_w = __popc(surv_mask & ((1u << lane) - 1u));
-    uint32_t nt_incl = nt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, nt_incl, o);
-        if (lane >= o) nt_incl += t;
-    }
-    if (lane == 31) {
-        s_wsurv[warp] = __popc(surv_mask);
-        s_wnt[warp] = nt_incl;
-    }
+    if (lane == 0) s_wsurv[warp] = __popc(surv_mask);
     __syncthreads();
-    uint32_t surv_before = 0, nt_before = 0, blk_surv = 0, blk_nt = 0;
+    uint32_t surv_before = 0, blk_surv = 0;
 #pragma unroll
     for (int w = 0; w < PRE_THREADS / 32; w++) {
-        const uint32_t a = s_wsurv[w], b = s_wnt[w];
-        if (w < warp) {
-            surv_before += a;
-            nt_before += b;
-        }
+        const uint32_t a = s_wsurv[w];
+        if (w < warp) surv_before += a;
         blk_surv += a;
-        blk_nt += b;
     }
-    const uint32_t local_rank = surv_before + surv_rank_w;      // compact slot within the chunk
-    const uint32_t local_off = nt_before + (nt_incl - nt);      // exclusive tile offset within the chunk
-
     // publish this chunk's aggregate as early as possible
-    if (tid == 0) st_status(P.status + chunk, st_pack(chunk == 0 ? ST_PREFIX : ST_AGG, blk_surv, blk_nt));
+    if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S1_PREFIX : S1_AGG) | blk_surv);
 
     // ---- SH colour of survivors (overlaps the look-back of other chunks) ----
     float colr = 0.f, colg = 0.f, colb = 0.f;
     if (surv) compute_sh(reinterpret_cast<const float4*>(P.sh) + (size_t)i * 12, px, py, pz, U.camera_position, colr, colg, colb);
 
-    // ---- decoupled look-back by warp 0 ----
+    // ---- decoupled look-back by warp 0: 32 predecessors per step ----
     if (warp == 0) {
-        uint32_t ex_s = 0;
-        unsigned long long ex_t = 0;
+        uint32_t ex = 0;
         if (chunk != 0) {
             int look = (int)chunk - 1;
             while (true) {
                 const int idx = look - lane;
-                unsigned long long st = ST_PREFIX;  // virtual predecessor of chunk 0
+                uint32_t st = S1_PREFIX;  // virtual predecessor of chunk 0
                 if (idx >= 0) {
-                    st = ld_status(P.status + idx);
-                    while ((st & ST_FLAGS) == 0) st = ld_status(P.status + idx);
+                    st = ld_vol(P.status + idx);
+                    while ((st & S1_FLAGS) == 0) st = ld_vol(P.status + idx);
                 }
-                const unsigned pm = __ballot_sync(FULL, (st & ST_FLAGS) == ST_PREFIX);
+                const unsigned pm = __ballot_sync(FULL, (st & S1_FLAGS) == S1_PREFIX);
                 const int first = pm ? (__ffs(pm) - 1) : 32;
-                uint32_t cs = (lane <= first) ? (uint32_t)((st >> 32) & 0x3fffffffu) : 0u;
-                unsigned long long ct = (lane <= first) ? (st & 0xffffffffull) : 0ull;
+                uint32_t cs = (lane <= first) ? (st & S1_COUNT) : 0u;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    cs += __shfl_xor_sync(FULL, cs, o);
-                    ct += __shfl_xor_sync(FULL, ct, o);
-                }
-                ex_s += cs;
-                ex_t += ct;
+                for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(FULL, cs, o);
+                ex += cs;
                 if (pm) break;
                 look -= 32;
             }
-            if (lane == 0) st_status(P.status + chunk, st_pack(ST_PREFIX, ex_s + blk_surv, ex_t + blk_nt));
+            if (lane == 0) st_vol(P.status + chunk, S1_PREFIX | (ex + blk_surv));
         }
         if (lane == 0) {
-            s_base_surv = ex_s;
-            s_base_tiles = ex_t;
-            if (chunk == num_chunks - 1) {  // global totals
-                const unsigned long long total = ex_t + blk_nt;
-                P.ctl->instances_total = total;
-                P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
-                P.ctl->overflow = total > P.capacity ? 1u : 0u;
-                P.ctl->num_visible = ex_s + blk_surv;
-            }
+            s_base_surv = ex;
+            if (chunk == num_chunks - 1) P.ctl->num_visible = ex + blk_surv;
         }
     }
-    s_off[tid] = local_off;
-    if (tid == 0) s_off[PRE_THREADS] = blk_nt;
     __syncthreads();
-    const uint32_t base_surv = s_base_surv;
-    const unsigned long long base_tiles = s_base_tiles;
 
-    // ---- compacted blend record + emission descriptors ----
-    const uint32_t cid = base_surv + local_rank;
+    // ---- compacted per-survivor outputs ----
     if (surv) {
+        const uint32_t cid = s_base_surv + surv_before + surv_rank_w;
         float4* rec = P.recs + (size_t)cid * 3;
         rec[0] = make_float4(uvx, uvy, conx, cony);
         rec[1] = make_float4(conz, opac, colr, colg);
         rec[2] = make_float4(colb, depth, radii, __uint_as_float(i));
-        s_info[tid] = make_uint4((uint32_t)bx0 | ((uint32_t)by0 << 16), (uint32_t)(by1 - by0), __float_as_uint(depth), cid);
+        P.einfo[cid] = make_uint2((uint32_t)bx0 | ((uint32_t)by0 << 16), (uint32_t)(bx1 - bx0) | ((uint32_t)(by1 - by0) << 16));
+        P.dkeys[cid] = __float_as_uint(depth);  // depth > 0.2: the IEEE bits are monotone as unsigned
+        P.dvals[cid] = cid;
     }
     if (DEBUG && i < P.n) {
         P.dbg_tiles[i] = nt;
-        const unsigned long long incl = base_tiles + local_off + nt;
-        P.dbg_scan[i] = (uint32_t)incl;
         P.dbg_aabb[i] = surv ? make_uint4(bx0, by0, bx1, by1) : make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
+}
 
-    // ---- block-cooperative key emission, preprocess_sort.comp:43-58 order ----
-    const uint32_t tileX = (uint32_t)tiles_x;
-    for (uint32_t j = tid; j < blk_nt; j += PRE_THREADS) {
-        int lo = 0, hi = PRE_THREADS - 1;  // smallest g with s_off[g + 1] > j
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid + 1] <= j) lo = mid + 1;
-            else hi = mid;
+// ------------------------------------------------------------------------------------------
+// k_emit
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ EmitParams P) {
+    __shared__ uint32_t s_chunk;
+    __shared__ uint32_t s_wnt[PRE_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_off[PRE_THREADS + 1];
+    __shared__ uint4 s_info[PRE_THREADS];  // x0 | y0 << 16, h, magic (ceil(2^32 / h), 0 = use a real divide), compact id
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nv = P.ctl->num_visible;
+    const uint32_t num_chunks = (nv + PRE_THREADS - 1) / PRE_THREADS;
+
+    while (true) {
+        if (tid == 0) s_chunk = atomicAdd(&P.ctl->emit_ticket, 1u);
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= num_chunks) break;
+        const uint32_t j = chunk * PRE_THREADS + tid;
+
+        uint32_t nt = 0, cid = 0, xy = 0, h = 1;
+        if (j < nv) {
+            cid = __ldg(P.sorted_cid + j);
+            const uint2 inf = __ldg(P.einfo + cid);
+            xy = inf.x;
+            h = inf.y >> 16;
+            nt = (inf.y & 0xffffu) * h;
         }
-        const uint4 inf = s_info[lo];
-        const uint32_t k = j - s_off[lo];
-        const uint32_t h = inf.y;
-        const uint32_t x = (inf.x & 0xffffu) + k / h;  // x outer (:47)
-        const uint32_t y = (inf.x >> 16) + k % h;      // y inner (:48)
-        const unsigned long long slot = base_tiles + j;
-        if (slot < P.capacity) {
-            P.keys[slot] = ((unsigned long long)(x + y * tileX) << 32) | inf.z;  // :49-54
-            P.vals[slot] = inf.w;                                               // compact id (orig idx in rec[2].w)
+        // ---- block scan of the tile counts (prefix_sum.comp's job) ----
+        uint32_t nt_incl = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, nt_incl, o);
+            if (lane >= o) nt_incl += t;
         }
+        if (lane == 31) s_wnt[warp] = nt_incl;
+        __syncthreads();
+        uint32_t nt_before = 0, blk_nt = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; w++) {
+            const uint32_t b = s_wnt[w];
+            if (w < warp) nt_before += b;
+            blk_nt += b;
+        }
+        const uint32_t local_off = nt_before + (nt_incl - nt);
+        if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
+
+        s_off[tid] = local_off;
+        if (tid == 0) s_off[PRE_THREADS] = blk_nt;
+        if (nt) {
+            // k / h by multiply-high: exact while k * h < 2^32 (k < nt); otherwise fall back to a divide
+            const uint32_t magic = (h > 1 && (unsigned long long)nt * h < (1ull << 32)) ? (uint32_t)((1ull << 32) / h) + 1u : 0u;
+            s_info[tid] = make_uint4(xy, h, magic, cid);
+        }
+
+        // ---- decoupled look-back by warp 0 ----
+        if (warp == 0) {
+            unsigned long long ex = 0;
+            if (chunk != 0) {
+                int look = (int)chunk - 1;
+                while (true) {
+                    const int idx = look - lane;
+                    unsigned long long st = S2_PREFIX;
+                    if (idx >= 0) {
+                        st = ld_vol(P.status + idx);
+                        while ((st & S2_FLAGS) == 0) st = ld_vol(P.status + idx);
+                    }
+                    const unsigned pm = __ballot_sync(FULL, (st & S2_FLAGS) == S2_PREFIX);
+                    const int first = pm ? (__ffs(pm) - 1) : 32;
+                    unsigned long long ct = (lane <= first) ? (st & S2_COUNT) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(FULL, ct, o);
+                    ex += ct;
+                    if (pm) break;
+                    look -= 32;
+                }
+                if (lane == 0) st_vol(P.status + chunk, S2_PREFIX | (ex + blk_nt));
+            }
+            if (lane == 0) {
+                s_base = ex;
+                if (chunk == num_chunks - 1) {  // global totals: M (Renderer.cpp:538 reads this back; we keep it in HBM)
+                    const unsigned long long total = ex + blk_nt;
+                    P.ctl->instances_total = total;
+                    P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
+                    P.ctl->overflow = total > P.capacity ? 1u : 0u;
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned long long base = s_base;
+
+        // ---- block-cooperative emission: coalesced stores, x outer / y inner inside a Gaussian (:47-48) ----
+        for (uint32_t o = tid; o < blk_nt; o += PRE_THREADS) {
+            int lo = 0, hi = PRE_THREADS - 1;  // smallest g with s_off[g + 1] > o
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid + 1] <= o) lo = mid + 1;
+                else hi = mid;
+            }
+            const uint4 inf = s_info[lo];
+            const uint32_t k = o - s_off[lo];
+            const uint32_t q = inf.y == 1 ? k : (inf.z ? __umulhi(k, inf.z) : k / inf.y);
+            const uint32_t x = (inf.x & 0xffffu) + q;
+            const uint32_t y = (inf.x >> 16) + (k - q * inf.y);
+            const unsigned long long slot = base + o;
+            if (slot < P.capacity) {
+                P.keys[slot] = x + y * P.tiles_x;  // :49 tile index (the high 32 bits of the reference key)
+                P.vals[slot] = inf.w;              // compact id (original index in rec[2].w)
+            }
+        }
+        __syncthreads();  // smem is reused by the next chunk
     }
 }
 
 }  // namespace
 
-cudaError_t launch_preprocess(const PreprocessParams& p, bool debug, cudaStream_t s) {
+cudaError_t launch_project(const ProjectParams& p, bool debug, cudaStream_t s) {
     if (p.n == 0) return cudaSuccess;
     const unsigned blocks = (p.n + PRE_THREADS - 1) / PRE_THREADS;
-    if (debug) k_preprocess<true><<<blocks, PRE_THREADS, 0, s>>>(p);
-    else k_preprocess<false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    if (debug) k_project<true><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else k_project<false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit(const EmitParams& p, cudaStream_t s) {
+    uint32_t blocks = (p.nv_hint + PRE_THREADS - 1) / PRE_THREADS;
+    const uint32_t cap = (uint32_t)p.num_sms * 8;  // ticket loop: any grid size is correct
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    k_emit<<<blocks, PRE_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -64,8 +64,9 @@ class Stats(C.Structure):
                 ("blend_consumed", C.c_uint64), ("instance_capacity", C.c_uint64), ("sort_passes", C.c_uint32),
                 ("regrow_count", C.c_uint32), ("preprocess_ms", C.c_float), ("prefix_sum_ms", C.c_float),
                 ("preprocess_sort_ms", C.c_float), ("sort_ms", C.c_float), ("tile_boundary_ms", C.c_float),
-                ("render_ms", C.c_float), ("frame_ms", C.c_float), ("sort_hist_ms", C.c_float),
-                ("sort_pass_ms", C.c_float * 8)]
+                ("render_ms", C.c_float), ("frame_ms", C.c_float), ("sort_depth_ms", C.c_float),
+                ("sort_tile_ms", C.c_float), ("sort_hist_ms", C.c_float), ("sort_pass_ms", C.c_float * 8),
+                ("sort_depth_passes", C.c_uint32), ("pad_", C.c_uint32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}

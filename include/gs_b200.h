@@ -82,29 +82,36 @@ typedef enum gsb_buffer {
     GSB_BUF_COV3D = 0,         /* scene->cov3DBuffer: N * 6 float                 (GSScene.cpp:158) */
     GSB_BUF_ATTR = 1,          /* vertexAttributeBuffer: N * gsb_vertex_attribute (Renderer.cpp:169); culled entries zero */
     GSB_BUF_TILES_OVERLAP = 2, /* tileOverlapBuffer: N * u32                      (Renderer.cpp:170) */
-    GSB_BUF_PREFIX_SUM = 3,    /* inclusive scan: N * u32                         (Renderer.cpp:215) */
-    GSB_BUF_KEYS_UNSORTED = 4, /* sortKBufferEven after preprocess_sort: M * u64  (Renderer.cpp:235) */
-    GSB_BUF_VALS_UNSORTED = 5, /* sortVBufferEven after preprocess_sort: M * u32  (Renderer.cpp:239) */
+    GSB_BUF_PREFIX_SUM = 3,    /* inclusive scan in Gaussian-index order: N * u32 (Renderer.cpp:215); derived on the
+                                  host from TILES_OVERLAP -- the device scans in depth order inside k_emit */
+    GSB_BUF_KEYS_UNSORTED = 4, /* sortKBuffer after the reference's radix pass 3 (bits 0-31 = depth sorted, tile
+                                  bits not yet): M * u64.  Equals preprocess_sort's output stably sorted by depth;
+                                  this implementation emits the instances directly in that order */
+    GSB_BUF_VALS_UNSORTED = 5, /* the payloads (Gaussian indices) that go with KEYS_UNSORTED: M * u32 */
     GSB_BUF_KEYS_SORTED = 6,   /* sortKBufferEven after the 8 passes: M * u64 */
     GSB_BUF_VALS_SORTED = 7,   /* sortVBufferEven after the 8 passes: M * u32 (Gaussian indices) */
     GSB_BUF_TILE_BOUNDARY = 8  /* tileBoundaryBuffer: T * 2 u32                   (Renderer.cpp:321) */
 } gsb_buffer;
 
 /* The reference's six timestamp pairs (src/Renderer.cpp:484-699) + its "instances" text metric
- * (:540).  preprocess/prefix_sum/preprocess_sort are ONE fused kernel here: its time is reported
- * under preprocess_ms and the other two are 0. */
+ * (:540).  Mapping: preprocess_ms = k_project; preprocess_sort_ms = k_emit (tile-count scan + key
+ * emission, so prefix_sum_ms is 0); sort_ms = Gaussian-level depth sort + instance-level tile sort. */
 typedef struct gsb_stats {
     uint64_t num_gaussians;     /* N */
     uint64_t num_visible;       /* N_v: survivors of the three culls */
     uint64_t num_instances;     /* M  ("instances", Renderer.cpp:540) */
     uint64_t blend_consumed;    /* sum over tiles of run entries read before the tile terminated */
     uint64_t instance_capacity; /* current arena capacity in instances */
-    uint32_t sort_passes;       /* P radix passes used for this frame */
+    uint32_t sort_passes;       /* radix passes of the instance-level (tile id) sort = ceil(log2(T) / 8) */
     uint32_t regrow_count;      /* times the arena was regrown and the frame re-rendered so far */
     float preprocess_ms, prefix_sum_ms, preprocess_sort_ms, sort_ms, tile_boundary_ms, render_ms;
     float frame_ms;         /* first kernel to last kernel of the frame */
-    float sort_hist_ms;     /* the one histogram kernel inside sort_ms */
-    float sort_pass_ms[8];  /* each Onesweep pass kernel inside sort_ms (first sort_passes entries) */
+    float sort_depth_ms;    /* Onesweep over the N_v visible Gaussians, 32-bit depth keys (histogram + passes) */
+    float sort_tile_ms;     /* Onesweep over the M instances, tile-id keys (histogram + passes) */
+    float sort_hist_ms;     /* the histogram kernel of the instance sort */
+    float sort_pass_ms[8];  /* each pass kernel of the instance sort (first sort_passes entries) */
+    uint32_t sort_depth_passes; /* passes of the Gaussian-level sort (4) */
+    uint32_t pad_;
 } gsb_stats;
 
 /* ---- lifetime: replaces Renderer::initializeVulkan + create*Pipeline (Renderer.cpp:119-155,166-364) ---- */
