@@ -248,7 +248,8 @@ def main():
         frame(i, sync=True)
         s = ctx.stats()
         d = s.as_dict()
-        for k in ("preprocess_ms", "sort_ms", "tile_boundary_ms", "render_ms", "frame_ms", "sort_hist_ms"):
+        for k in ("preprocess_ms", "preprocess_sort_ms", "sort_ms", "sort_depth_ms", "sort_tile_ms", "tile_boundary_ms", "render_ms",
+                  "frame_ms", "sort_hist_ms"):
             stage_acc.setdefault(k, []).append(d[k])
         stage_acc.setdefault("sort_pass_ms", []).append(float(np.mean(d["sort_pass_ms"])) if d["sort_pass_ms"] else 0.0)
         m_acc.append(s.num_instances)
@@ -296,19 +297,23 @@ def main():
         peak, peak_src = measured_peak_gbs()
         nv = NV
         # algorithmic bytes per launch (SURVEY 8d / DESIGN.md), one launch = one frame's worth of that kernel
+        T_tiles = ((W + 15) // 16) * tiles_y
+        kd = "sort_depth(hist+4 onesweep passes over N_v)"
         alg = {
-            "k_preprocess": wl["n"] * 40 + nv * 192 + nv * 48 + 12 * M,       # scene read + SH of survivors + 48-B records + keys/payloads
-            "k_sort_hist": 8 * M,
-            "k_onesweep_pass": 24 * M,                                        # 12 B read + 12 B written per key
-            "k_tile_ranges": 8 * M + 8 * ((W + 15) // 16) * tiles_y,
+            "k_project": wl["n"] * 40 + nv * 192 + nv * (48 + 8 + 8),  # scene read + SH of survivors + record/AABB/depth key+payload
+            kd: nv * (4 + 16 * 4),                                     # histogram read + 4 x (8 B read + 8 B written)
+            "k_emit": nv * (4 + 8) + 8 * M,                            # sorted ids + AABBs in, (tile id, payload) out
+            "k_sort_hist": 4 * M,
+            "k_onesweep_pass": 16 * M,                                 # 8 B read + 8 B written per (tile id, payload) pair
+            "k_tile_ranges": 4 * M + 8 * T_tiles,
             "k_blend": CONS * (4 + 36) + (nrows if world == 1 else H) * W * bpp,
         }
-        dur = {"k_preprocess": stage["preprocess_ms"], "k_sort_hist": stage["sort_hist_ms"],
-               "k_onesweep_pass": stage["sort_pass_ms"], "k_tile_ranges": stage["tile_boundary_ms"], "k_blend": stage["render_ms"]}
-        share = {"k_preprocess": stage["preprocess_ms"], "k_sort_hist": stage["sort_hist_ms"],
-                 "k_onesweep_pass": stage["sort_pass_ms"] * passes, "k_tile_ranges": stage["tile_boundary_ms"],
-                 "k_blend": stage["render_ms"]}
-        kern = {k: {"ms_per_launch": dur[k], "launches_per_step": passes if k == "k_onesweep_pass" else 1,
+        dur = {"k_project": stage["preprocess_ms"], kd: stage["sort_depth_ms"], "k_emit": stage["preprocess_sort_ms"],
+               "k_sort_hist": stage["sort_hist_ms"], "k_onesweep_pass": stage["sort_pass_ms"],
+               "k_tile_ranges": stage["tile_boundary_ms"], "k_blend": stage["render_ms"]}
+        share = dict(dur)
+        share["k_onesweep_pass"] = stage["sort_pass_ms"] * passes
+        kern = {k: {"ms_per_launch": dur[k], "launches_per_step": passes if k == "k_onesweep_pass" else (5 if k == kd else 1),
                     "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (dur[k] * 1e-3) / 1e9 if dur[k] > 0 else None,
                     "share_of_step": share[k] / stage["frame_ms"] if stage["frame_ms"] > 0 else None} for k in alg}
         dom = max(share, key=share.get)
@@ -326,7 +331,7 @@ def main():
                        "parallelism": f"tile-row bands x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 160,
                     "d2h_bytes_per_step": int(nrows * W * bpp) + 64, "api": "gsb_render(host UBO -> host BGRA8), synchronous per frame"},
-            "gpu_launches": int((4 + passes) * args.steps),
+            "gpu_launches": int((10 + passes) * args.steps),  # project, hist+4 passes (depth), emit, hist+P passes (tile), ranges, blend
             "clocks": clocks,
             "roofline": roof,
             "kernels": kern,
