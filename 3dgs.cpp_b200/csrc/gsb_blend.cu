@@ -2,9 +2,15 @@
 // Replaces render.comp:30-99 (dispatch src/Renderer.cpp:654-677).  The reference makes every
 // pixel thread gather idx + uv + conic + colour from global memory for every Gaussian of the
 // tile's run (render.comp:62-65,87; README.md:87 lists staging as a TODO).  Here one CTA owns one
-// tile, stages the run in batches of 256 compact 48-B records into shared memory once, and all
-// 256 pixel threads then read each record as a shared-memory broadcast.  The per-pixel `break`
-// (render.comp:83-85) becomes a per-thread done flag + a block-wide vote per batch.
+// tile and
+//   * stages the run in batches of 256 compact 48-B records into shared memory once;
+//   * while staging, each thread classifies its Gaussian against the eight 8x4-pixel blocks of
+//     the tile (one block per warp): a block whose best-case exponent is below the shader's own
+//     alpha < 1/255 cut (with an fp32 error margin) can never contribute, so that warp never
+//     touches the record (bit-identical result: those pairs hit `continue` in render.comp:78);
+//   * each warp compacts the batch with one ballot per 32 records and walks only its survivors,
+//     reading each record as a shared-memory broadcast.
+// The per-pixel `break` (render.comp:83-85) becomes a per-lane done flag + warp / block votes.
 //
 // EXACT mode: -fmad=false, ops in render.comp's order, exp = the fixed IEEE sequence below
 // (bit-identical to oracle exp-mode 1).  FAST mode: explicit FMA + ex2.approx.
@@ -15,6 +21,8 @@ namespace gsb {
 namespace {
 
 constexpr int BLEND_THREADS = 256;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float POWER_CUT = -5.55f;  // alpha = opacity * exp(power) <= exp(-5.55) < 1/255 because opacity <= 1
 
 // Bit-defined exp for x in [-87, 0]; mirrors gso_exp_shared() in oracle/gs_oracle.c op for op.
 __device__ __forceinline__ float exp_shared(float x) {
@@ -40,20 +48,66 @@ __device__ __forceinline__ uint32_t unorm8(float v) {
     return __float2uint_rn(v * 255.0f);
 }
 
+// Minimum over [lo, hi] of the 1-D quadratic  q(t) = a t^2 + 2 b t + c  (a > 0, inv_a ~ 1/a).
+// An inexact minimiser only moves the result by a (t - t*)^2, second order in the rounding error.
+__device__ __forceinline__ float min_quad_1d(float a, float inv_a, float b, float c, float lo, float hi) {
+    const float t = fminf(fmaxf(-b * inv_a, lo), hi);
+    return fmaf(fmaf(a, t, 2.0f * b), t, c);
+}
+
+// Bit w set <=> warp w's 8x4 pixel block may receive a contribution from this Gaussian.
+// q(dx, dy) = A dx^2 + 2 B dx dy + C dy^2 is minimised over the block's (continuous) rectangle; the exponent can
+// not exceed -q_min / 2 there.  The block is dropped only if that bound, widened by a bound on the fp32 rounding
+// error of render.comp:66's evaluation order, is still below POWER_CUT -- so a dropped pair is one the shader
+// itself skips (alpha < 1/255) and the image is bit-identical.
+__device__ __forceinline__ uint32_t block_mask(float ux, float uy, float A, float B, float C, float tile_x0, float tile_y0) {
+    if (!(A > 0.0f) || !(C > 0.0f)) return 0xffu;  // not positive definite / NaN: never cull
+    const float inv_a = __frcp_rn(A), inv_c = __frcp_rn(C);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const float x0 = tile_x0 + (float)((w & 1) * 8), y0 = tile_y0 + (float)((w >> 1) * 4);
+        // d = uv - pixel, pixel in [x0, x0+7] x [y0, y0+3]
+        const float dx_lo = ux - (x0 + 7.0f), dx_hi = ux - x0, dy_lo = uy - (y0 + 3.0f), dy_hi = uy - y0;
+        float qmin;
+        if (dx_lo <= 0.0f && dx_hi >= 0.0f && dy_lo <= 0.0f && dy_hi >= 0.0f) {
+            qmin = 0.0f;  // centre inside the block
+        } else {
+            // convex => the minimum over the rectangle lies on its boundary: four 1-D problems
+            const float e0 = min_quad_1d(C, inv_c, B * dx_lo, A * dx_lo * dx_lo, dy_lo, dy_hi);  // dx = dx_lo
+            const float e1 = min_quad_1d(C, inv_c, B * dx_hi, A * dx_hi * dx_hi, dy_lo, dy_hi);  // dx = dx_hi
+            const float e2 = min_quad_1d(A, inv_a, B * dy_lo, C * dy_lo * dy_lo, dx_lo, dx_hi);  // dy = dy_lo
+            const float e3 = min_quad_1d(A, inv_a, B * dy_hi, C * dy_hi * dy_hi, dx_lo, dx_hi);  // dy = dy_hi
+            qmin = fminf(fminf(e0, e1), fminf(e2, e3));
+        }
+        const float dxm = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), dym = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
+        const float mag = 0.5f * (A * dxm * dxm + C * dym * dym) + fabsf(B) * dxm * dym;  // sum of |terms| of :66
+        const float margin = 0.02f + 2e-6f * mag;  // >= 32 ulp of the largest term: covers both evaluations' rounding
+        if (!(-0.5f * qmin < POWER_CUT - margin)) mask |= 1u << w;  // NaN -> keep
+    }
+    return mask;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__ BlendParams P) {
-    __shared__ float4 s_r0[BLEND_THREADS];  // uv.x uv.y conic.x conic.y
-    __shared__ float4 s_r1[BLEND_THREADS];  // conic.z opacity r g
+    // staged with exact sign / power-of-two scalings so that render.comp:66 needs one multiply less and rounds identically:
+    //   -0.5 * ((A dx) dx + (C dy) dy) - (B dx) dy  ==  ((-A/2 dx) dx + (-C/2 dy) dy) + ((-B) dx) dy   (bit for bit)
+    __shared__ float4 s_r0[BLEND_THREADS];  // uv.x uv.y -conic.x/2 -conic.y
+    __shared__ float4 s_r1[BLEND_THREADS];  // -conic.z/2 opacity r g
     __shared__ float s_b[BLEND_THREADS];    // b
+    __shared__ uint32_t s_mask[BLEND_THREADS];
     __shared__ uint32_t s_used;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % P.tiles_x;
     const uint32_t ty = P.tile_row_begin + blockIdx.x / P.tiles_x;
     const uint2 range = P.ranges[ty * P.tiles_x + tx];  // render.comp:43-44
-    const uint32_t px = tx * GSB_TILE + (tid & 15), py = ty * GSB_TILE + (tid >> 4);
+    // warp w owns the 8x4 pixel block at (8 * (w & 1), 4 * (w >> 1)) of the tile
+    const uint32_t px = tx * GSB_TILE + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = ty * GSB_TILE + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < P.width && py < P.height;  // :37-39
     const float fx = (float)px, fy = (float)py;
+    const float tile_x0 = (float)(tx * GSB_TILE), tile_y0 = (float)(ty * GSB_TILE);
     if (tid == 0) s_used = 0;
     __syncthreads();
 
@@ -66,48 +120,54 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
         if ((uint32_t)tid < cnt) {
             const uint32_t cid = __ldg(P.vals + base + tid);
             const float4* rec = P.recs + (size_t)cid * 3;
-            s_r0[tid] = __ldg(rec);
-            s_r1[tid] = __ldg(rec + 1);
+            const float4 a = __ldg(rec), b = __ldg(rec + 1);
+            s_r0[tid] = make_float4(a.x, a.y, -0.5f * a.z, -a.w);
+            s_r1[tid] = make_float4(-0.5f * b.x, b.y, b.z, b.w);
             s_b[tid] = __ldg(reinterpret_cast<const float*>(rec + 2));
+            s_mask[tid] = block_mask(a.x, a.y, a.z, a.w, b.x, tile_x0, tile_y0);
         }
         __syncthreads();
-        if (!done) {
-            uint32_t j = 0;
-            for (; j < cnt; j++) {
-                const float4 a = s_r0[j];
-                const float4 b = s_r1[j];
-                const float dx = a.x - fx, dy = a.y - fy;  // :64
-                float alpha;
-                if (MODE == GSB_MODE_EXACT) {
-                    const float power = -0.5f * ((a.z * dx) * dx + (b.x * dy) * dy) - (a.w * dx) * dy;  // :66
-                    if (power > 0.0f) continue;   // :68-70
-                    if (power < -5.55f) continue;  // alpha <= exp(-5.55) < 1/255 because opacity <= 1
-                    alpha = fminf(0.99f, b.y * exp_shared(power));  // :77
-                } else {
-                    const float q = fmaf(a.z * dx, dx, (b.x * dy) * dy);
-                    const float power = fmaf(-0.5f, q, -(a.w * dx) * dy);
-                    if (power > 0.0f) continue;
-                    if (power < -5.55f) continue;
-                    alpha = fminf(0.99f, b.y * __expf(power));
+        if (!__all_sync(FULL, done)) {
+            for (uint32_t c = 0; c < cnt; c += 32) {
+                const uint32_t mk = (c + lane < cnt) ? s_mask[c + lane] : 0u;
+                unsigned bits = __ballot_sync(FULL, (mk >> warp) & 1u);
+                while (bits) {
+                    const uint32_t j = c + (uint32_t)__ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    if (done) continue;
+                    const float4 a = s_r0[j];
+                    const float4 b = s_r1[j];
+                    const float dx = a.x - fx, dy = a.y - fy;  // :64
+                    float alpha;
+                    if (MODE == GSB_MODE_EXACT) {
+                        const float power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
+                        if (power > 0.0f || power < POWER_CUT) continue;  // :68-70; < POWER_CUT implies alpha < 1/255 (:78); NaN falls through like the shader
+                        alpha = fminf(0.99f, b.y * exp_shared(power));  // :77
+                    } else {
+                        const float power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
+                        if (power > 0.0f || power < POWER_CUT) continue;
+                        alpha = fminf(0.99f, b.y * __expf(power));
+                    }
+                    if (alpha < 1.0f / 255.0f) continue;      // :78-80
+                    const float test_T = T * (1.0f - alpha);  // :82
+                    if (test_T < 0.0001f) {                   // :83-85
+                        done = true;
+                        used = base - range.x + j + 1;
+                        continue;
+                    }
+                    if (MODE == GSB_MODE_EXACT) {
+                        c0 = c0 + (b.z * alpha) * T;  // :87
+                        c1 = c1 + (b.w * alpha) * T;
+                        c2 = c2 + (s_b[j] * alpha) * T;
+                    } else {
+                        const float w = alpha * T;
+                        c0 = fmaf(b.z, w, c0);
+                        c1 = fmaf(b.w, w, c1);
+                        c2 = fmaf(s_b[j], w, c2);
+                    }
+                    T = test_T;  // :88
                 }
-                if (alpha < 1.0f / 255.0f) continue;  // :78-80
-                const float test_T = T * (1.0f - alpha);  // :82
-                if (test_T < 0.0001f) {                   // :83-85
-                    done = true;
-                    used = base - range.x + j + 1;
-                    break;
-                }
-                if (MODE == GSB_MODE_EXACT) {
-                    c0 = c0 + (b.z * alpha) * T;  // :87
-                    c1 = c1 + (b.w * alpha) * T;
-                    c2 = c2 + (s_b[j] * alpha) * T;
-                } else {
-                    const float w = alpha * T;
-                    c0 = fmaf(b.z, w, c0);
-                    c1 = fmaf(b.w, w, c1);
-                    c2 = fmaf(s_b[j], w, c2);
-                }
-                T = test_T;  // :88
+                if (__all_sync(FULL, done)) break;
             }
             if (!done) used = base - range.x + cnt;
         }
