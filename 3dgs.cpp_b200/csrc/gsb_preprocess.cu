@@ -293,31 +293,41 @@ __global__ void __launch_bounds__(PRE_THREADS) k_project(const __grid_constant__
 // ------------------------------------------------------------------------------------------
 // k_emit
 // ------------------------------------------------------------------------------------------
+constexpr int EMIT_WIN = 4096;   // instances staged in shared memory per window
+constexpr uint32_t EMIT_BIG = 128;  // Gaussians covering more tiles than this are expanded by the whole block
+
 __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ EmitParams P) {
     __shared__ uint32_t s_chunk;
     __shared__ uint32_t s_wnt[PRE_THREADS / 32];
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_off[PRE_THREADS + 1];
-    __shared__ uint4 s_info[PRE_THREADS];  // x0 | y0 << 16, h, magic (ceil(2^32 / h), 0 = use a real divide), compact id
+    __shared__ uint32_t s_nbig;
+    __shared__ uint32_t s_big[PRE_THREADS];  // lanes of the chunk holding "big" Gaussians
+    __shared__ uint4 s_info[PRE_THREADS];    // x0 | y0 << 16, w | h << 16, local offset, compact id
+    __shared__ uint32_t s_key[EMIT_WIN];
+    __shared__ uint32_t s_val[EMIT_WIN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nv = P.ctl->num_visible;
     const uint32_t num_chunks = (nv + PRE_THREADS - 1) / PRE_THREADS;
+    const uint32_t tiles_x = P.tiles_x;
 
     while (true) {
-        if (tid == 0) s_chunk = atomicAdd(&P.ctl->emit_ticket, 1u);
+        if (tid == 0) {
+            s_chunk = atomicAdd(&P.ctl->emit_ticket, 1u);
+            s_nbig = 0;
+        }
         __syncthreads();
         const uint32_t chunk = s_chunk;
         if (chunk >= num_chunks) break;
         const uint32_t j = chunk * PRE_THREADS + tid;
 
-        uint32_t nt = 0, cid = 0, xy = 0, h = 1;
+        uint32_t nt = 0, cid = 0, xy = 0, wh = 0;
         if (j < nv) {
             cid = __ldg(P.sorted_cid + j);
             const uint2 inf = __ldg(P.einfo + cid);
             xy = inf.x;
-            h = inf.y >> 16;
-            nt = (inf.y & 0xffffu) * h;
+            wh = inf.y;
+            nt = (wh & 0xffffu) * (wh >> 16);
         }
         // ---- block scan of the tile counts (prefix_sum.comp's job) ----
         uint32_t nt_incl = nt;
@@ -335,73 +345,94 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
             if (w < warp) nt_before += b;
             blk_nt += b;
         }
-        const uint32_t local_off = nt_before + (nt_incl - nt);
+        const uint32_t off = nt_before + (nt_incl - nt);  // exclusive offset inside the chunk
         if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
-
-        s_off[tid] = local_off;
-        if (tid == 0) s_off[PRE_THREADS] = blk_nt;
-        if (nt) {
-            // k / h by multiply-high: exact while k * h < 2^32 (k < nt); otherwise fall back to a divide
-            const uint32_t magic = (h > 1 && (unsigned long long)nt * h < (1ull << 32)) ? (uint32_t)((1ull << 32) / h) + 1u : 0u;
-            s_info[tid] = make_uint4(xy, h, magic, cid);
+        if (nt > EMIT_BIG) {
+            s_info[tid] = make_uint4(xy, wh, off, cid);
+            s_big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
         }
 
-        // ---- decoupled look-back by warp 0 ----
-        if (warp == 0) {
-            unsigned long long ex = 0;
-            if (chunk != 0) {
-                int look = (int)chunk - 1;
-                while (true) {
-                    const int idx = look - lane;
-                    unsigned long long st = S2_PREFIX;
-                    if (idx >= 0) {
-                        st = ld_vol(P.status + idx);
-                        while ((st & S2_FLAGS) == 0) st = ld_vol(P.status + idx);
-                    }
-                    const unsigned pm = __ballot_sync(FULL, (st & S2_FLAGS) == S2_PREFIX);
-                    const int first = pm ? (__ffs(pm) - 1) : 32;
-                    unsigned long long ct = (lane <= first) ? (st & S2_COUNT) : 0ull;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(FULL, ct, o);
-                    ex += ct;
-                    if (pm) break;
-                    look -= 32;
-                }
-                if (lane == 0) st_vol(P.status + chunk, S2_PREFIX | (ex + blk_nt));
-            }
-            if (lane == 0) {
-                s_base = ex;
-                if (chunk == num_chunks - 1) {  // global totals: M (Renderer.cpp:538 reads this back; we keep it in HBM)
-                    const unsigned long long total = ex + blk_nt;
-                    P.ctl->instances_total = total;
-                    P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
-                    P.ctl->overflow = total > P.capacity ? 1u : 0u;
-                }
-            }
-        }
         __syncthreads();
-        const unsigned long long base = s_base;
+        const uint32_t nbig = s_nbig;
+        unsigned long long base = 0;
 
-        // ---- block-cooperative emission: coalesced stores, x outer / y inner inside a Gaussian (:47-48) ----
-        for (uint32_t o = tid; o < blk_nt; o += PRE_THREADS) {
-            int lo = 0, hi = PRE_THREADS - 1;  // smallest g with s_off[g + 1] > o
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_off[mid + 1] <= o) lo = mid + 1;
-                else hi = mid;
+        // ---- expansion through shared memory, window by window; x outer / y inner inside a Gaussian (:47-48) ----
+        const uint32_t x0 = xy & 0xffffu, y0 = xy >> 16, h = wh >> 16;
+        for (uint32_t w0 = 0; w0 == 0 || w0 < blk_nt; w0 += EMIT_WIN) {  // at least once: the look-back lives inside
+            const uint32_t w1 = min(blk_nt, w0 + (uint32_t)EMIT_WIN);
+            if (nt != 0 && nt <= EMIT_BIG) {  // small Gaussians: each thread writes its own tiles
+                const uint32_t lo = max(off, w0), hi = min(off + nt, w1);
+                if (lo < hi) {
+                    uint32_t k = lo - off;
+                    uint32_t q = k / h, r = k - q * h;
+                    uint32_t t = (x0 + q) + (y0 + r) * tiles_x;
+                    for (uint32_t o = lo; o < hi; o++) {
+                        s_key[o - w0] = t;  // :49 tile index (the high 32 bits of the reference key)
+                        s_val[o - w0] = cid;
+                        t += tiles_x;
+                        if (++r == h) {  // next column: y back to y0, x + 1
+                            r = 0;
+                            t = t - h * tiles_x + 1;
+                        }
+                    }
+                }
             }
-            const uint4 inf = s_info[lo];
-            const uint32_t k = o - s_off[lo];
-            const uint32_t q = inf.y == 1 ? k : (inf.z ? __umulhi(k, inf.z) : k / inf.y);
-            const uint32_t x = (inf.x & 0xffffu) + q;
-            const uint32_t y = (inf.x >> 16) + (k - q * inf.y);
-            const unsigned long long slot = base + o;
-            if (slot < P.capacity) {
-                P.keys[slot] = x + y * P.tiles_x;  // :49 tile index (the high 32 bits of the reference key)
-                P.vals[slot] = inf.w;              // compact id (original index in rec[2].w)
+            for (uint32_t b = 0; b < nbig; b++) {  // big Gaussians: the whole block expands each one
+                const uint4 inf = s_info[s_big[b]];
+                const uint32_t bh = inf.y >> 16, bnt = (inf.y & 0xffffu) * bh;
+                const uint32_t lo = max(inf.z, w0), hi = min(inf.z + bnt, w1);
+                for (uint32_t o = lo + tid; o < hi; o += PRE_THREADS) {
+                    const uint32_t k = o - inf.z, q = k / bh, r = k - q * bh;
+                    s_key[o - w0] = ((inf.x & 0xffffu) + q) + ((inf.x >> 16) + r) * tiles_x;
+                    s_val[o - w0] = inf.w;
+                }
             }
+            if (w0 == 0) {  // the look-back runs after the first fill so the predecessors' latency overlaps local work
+            // ---- decoupled look-back by warp 0 ----
+            if (warp == 0) {
+                unsigned long long ex = 0;
+                if (chunk != 0) {
+                    int look = (int)chunk - 1;
+                    while (true) {
+                        const int idx = look - lane;
+                        unsigned long long st = S2_PREFIX;
+                        if (idx >= 0) {
+                            st = ld_vol(P.status + idx);
+                            while ((st & S2_FLAGS) == 0) st = ld_vol(P.status + idx);
+                        }
+                        const unsigned pm = __ballot_sync(FULL, (st & S2_FLAGS) == S2_PREFIX);
+                        const int first = pm ? (__ffs(pm) - 1) : 32;
+                        unsigned long long ct = (lane <= first) ? (st & S2_COUNT) : 0ull;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(FULL, ct, o);
+                        ex += ct;
+                        if (pm) break;
+                        look -= 32;
+                    }
+                    if (lane == 0) st_vol(P.status + chunk, S2_PREFIX | (ex + blk_nt));
+                }
+                if (lane == 0) {
+                    s_base = ex;
+                    if (chunk == num_chunks - 1) {  // global totals: M (Renderer.cpp:538 reads this back; we keep it in HBM)
+                        const unsigned long long total = ex + blk_nt;
+                        P.ctl->instances_total = total;
+                        P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
+                        P.ctl->overflow = total > P.capacity ? 1u : 0u;
+                    }
+                }
+            }
+            }
+            __syncthreads();
+            if (w0 == 0) base = s_base;
+            for (uint32_t i = tid; i < w1 - w0; i += PRE_THREADS) {  // coalesced copy-out
+                const unsigned long long slot = base + w0 + i;
+                if (slot < P.capacity) {
+                    P.keys[slot] = s_key[i];
+                    P.vals[slot] = s_val[i];  // compact id (original index in rec[2].w)
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();  // smem is reused by the next chunk
     }
 }
 
