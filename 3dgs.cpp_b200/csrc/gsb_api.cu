@@ -59,6 +59,7 @@ struct gsb_ctx {
     int mode = GSB_MODE_EXACT;
     bool debug = false;
     bool timers = true;
+    bool tile_cull = false;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_sort[9] = {};  // instance sort: after hist, after each pass
     cudaEvent_t ev_done = nullptr;
@@ -243,6 +244,8 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     ep.status = ctx->emit_status;
     ep.ctl = ctx->ctl;
     ep.num_sms = ctx->num_sms;
+    ep.recs = ctx->recs;
+    ep.cull = ctx->tile_cull ? 1 : 0;
     CK(launch_emit(ep, stream));
     if (ctx->timers) CK(cudaEventRecord(ctx->ev[3], stream));
 
@@ -523,6 +526,12 @@ int gsb_set_debug(gsb_ctx* ctx, int debug) {
     return GSB_OK;
 }
 
+int gsb_set_tile_cull(gsb_ctx* ctx, int enabled) {
+    if (!ctx) return GSB_ERR_INVALID;
+    ctx->tile_cull = enabled != 0;
+    return GSB_OK;
+}
+
 int gsb_set_timers(gsb_ctx* ctx, int enabled) {
     if (!ctx) return GSB_ERR_INVALID;
     ctx->timers = enabled != 0;
@@ -609,6 +618,7 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
     out->num_gaussians = ctx->n;
     out->num_visible = c->num_visible;
     out->num_instances = c->instances_total;
+    out->num_instances_aabb = c->candidates_total;
     out->blend_consumed = c->blend_consumed;
     out->instance_capacity = ctx->capacity;
     out->sort_passes = ctx->last_passes;

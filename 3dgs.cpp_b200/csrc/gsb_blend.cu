@@ -14,6 +14,7 @@
 //
 // EXACT mode: -fmad=false, ops in render.comp's order, exp = the fixed IEEE sequence below
 // (bit-identical to oracle exp-mode 1).  FAST mode: explicit FMA + ex2.approx.
+#include "gsb_cull.cuh"
 #include "gsb_internal.cuh"
 
 namespace gsb {
@@ -22,7 +23,6 @@ namespace {
 
 constexpr int BLEND_THREADS = 256;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr float POWER_CUT = -5.55f;  // alpha = opacity * exp(power) <= exp(-5.55) < 1/255 because opacity <= 1
 
 // Bit-defined exp for x in [-87, 0]; mirrors gso_exp_shared() in oracle/gs_oracle.c op for op.
 __device__ __forceinline__ float exp_shared(float x) {
@@ -48,18 +48,7 @@ __device__ __forceinline__ uint32_t unorm8(float v) {
     return __float2uint_rn(v * 255.0f);
 }
 
-// Minimum over [lo, hi] of the 1-D quadratic  q(t) = a t^2 + 2 b t + c  (a > 0, inv_a ~ 1/a).
-// An inexact minimiser only moves the result by a (t - t*)^2, second order in the rounding error.
-__device__ __forceinline__ float min_quad_1d(float a, float inv_a, float b, float c, float lo, float hi) {
-    const float t = fminf(fmaxf(-b * inv_a, lo), hi);
-    return fmaf(fmaf(a, t, 2.0f * b), t, c);
-}
-
-// Bit w set <=> warp w's 8x4 pixel block may receive a contribution from this Gaussian.
-// q(dx, dy) = A dx^2 + 2 B dx dy + C dy^2 is minimised over the block's (continuous) rectangle; the exponent can
-// not exceed -q_min / 2 there.  The block is dropped only if that bound, widened by a bound on the fp32 rounding
-// error of render.comp:66's evaluation order, is still below POWER_CUT -- so a dropped pair is one the shader
-// itself skips (alpha < 1/255) and the image is bit-identical.
+// Bit w set <=> warp w's 8x4 pixel block may receive a contribution from this Gaussian (gsb_cull.cuh).
 __device__ __forceinline__ uint32_t block_mask(float ux, float uy, float A, float B, float C, float tile_x0, float tile_y0) {
     if (!(A > 0.0f) || !(C > 0.0f)) return 0xffu;  // not positive definite / NaN: never cull
     const float inv_a = __frcp_rn(A), inv_c = __frcp_rn(C);
@@ -67,23 +56,7 @@ __device__ __forceinline__ uint32_t block_mask(float ux, float uy, float A, floa
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         const float x0 = tile_x0 + (float)((w & 1) * 8), y0 = tile_y0 + (float)((w >> 1) * 4);
-        // d = uv - pixel, pixel in [x0, x0+7] x [y0, y0+3]
-        const float dx_lo = ux - (x0 + 7.0f), dx_hi = ux - x0, dy_lo = uy - (y0 + 3.0f), dy_hi = uy - y0;
-        float qmin;
-        if (dx_lo <= 0.0f && dx_hi >= 0.0f && dy_lo <= 0.0f && dy_hi >= 0.0f) {
-            qmin = 0.0f;  // centre inside the block
-        } else {
-            // convex => the minimum over the rectangle lies on its boundary: four 1-D problems
-            const float e0 = min_quad_1d(C, inv_c, B * dx_lo, A * dx_lo * dx_lo, dy_lo, dy_hi);  // dx = dx_lo
-            const float e1 = min_quad_1d(C, inv_c, B * dx_hi, A * dx_hi * dx_hi, dy_lo, dy_hi);  // dx = dx_hi
-            const float e2 = min_quad_1d(A, inv_a, B * dy_lo, C * dy_lo * dy_lo, dx_lo, dx_hi);  // dy = dy_lo
-            const float e3 = min_quad_1d(A, inv_a, B * dy_hi, C * dy_hi * dy_hi, dx_lo, dx_hi);  // dy = dy_hi
-            qmin = fminf(fminf(e0, e1), fminf(e2, e3));
-        }
-        const float dxm = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), dym = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
-        const float mag = 0.5f * (A * dxm * dxm + C * dym * dym) + fabsf(B) * dxm * dym;  // sum of |terms| of :66
-        const float margin = 0.02f + 2e-6f * mag;  // >= 32 ulp of the largest term: covers both evaluations' rounding
-        if (!(-0.5f * qmin < POWER_CUT - margin)) mask |= 1u << w;  // NaN -> keep
+        if (rect_may_contribute(ux, uy, A, B, C, inv_a, inv_c, x0, y0, 8.0f, 4.0f)) mask |= 1u << w;
     }
     return mask;
 }

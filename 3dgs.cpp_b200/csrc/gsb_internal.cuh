@@ -41,6 +41,7 @@ struct Control {
     uint32_t pad0[3];
     unsigned long long instances_total;  // unclamped M
     unsigned long long blend_consumed;
+    unsigned long long candidates_total;  // AABB instances before tile culling (the reference's M)
     SortCtl sort_depth;        // Gaussian-level sort (32-bit depth keys)
     SortCtl sort_tile;         // instance-level sort (tile-id keys); also used by gsb_sort_pairs
 };
@@ -76,6 +77,8 @@ struct EmitParams {
     unsigned long long* status;  // decoupled look-back words, one per 256-survivor chunk
     Control* ctl;
     int num_sms;
+    const float4* recs;          // blend records (centre + conic) for the optional instance culling
+    int cull;                    // gsb_set_tile_cull
 };
 
 cudaError_t launch_cov3d(const float* vtx_aos, uint64_t count, uint64_t dst_offset, float4* pos_op,

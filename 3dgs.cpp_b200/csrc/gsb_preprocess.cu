@@ -14,6 +14,7 @@
 //
 // Arithmetic: compiled with -fmad=false; every fp32 operation is a single IEEE op in the order
 // of the GLSL source, so results are value-identical to the oracle (bit-exact parity).
+#include "gsb_cull.cuh"
 #include "gsb_internal.cuh"
 
 namespace gsb {
@@ -346,7 +347,10 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
             blk_nt += b;
         }
         const uint32_t off = nt_before + (nt_incl - nt);  // exclusive offset inside the chunk
-        if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
+        if (tid == 0) {
+            st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
+            atomicAdd(&P.ctl->candidates_total, (unsigned long long)blk_nt);
+        }
         if (nt > EMIT_BIG) {
             s_info[tid] = make_uint4(xy, wh, off, cid);
             s_big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
@@ -436,6 +440,241 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_emit_cull -- k_emit with exact instance culling (gsb_set_tile_cull).  A (Gaussian, tile) instance
+// is dropped when the Gaussian provably cannot reach alpha >= 1/255 on any pixel of the 16x16 tile: the
+// blend would `continue` over it for all 256 pixels (render.comp:78), so the image is bit-identical, but
+// scan / sort / ranges / blend staging see fewer instances.  The reference has no such cull
+// (preprocess_sort.comp emits the whole AABB), so M and the key buffers differ from it when enabled.
+//
+// The set {q <= c} (q = the conic's quadratic form, c = 2 * (|POWER_CUT| + rounding margin)) is an ellipse;
+// intersected with one tile row (a slab of pixel-centre ordinates) it is convex, so the tiles of that row it
+// touches are exactly one contiguous span [xa, xb], computed in closed form per row (no per-tile test):
+//   dx_max(dy) = (-B dy + sqrt(A c - det dy^2)) / A  is concave with its maximum at dy* = -(B/C) sqrt(c C / det),
+// so over the slab it is attained at dy* clamped to the slab (and to |dy| <= sqrt(A c / det)); same for the minimum.
+// Emission order inside one Gaussian becomes row-major; that cannot change the sorted result (all instances of a
+// Gaussian have distinct tiles).  Gaussians covering more than EMIT_BIG tiles are emitted un-culled by the block.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long emit_lookback(unsigned long long* status, uint32_t chunk, int lane,
+                                                             unsigned long long blk_total) {
+    unsigned long long ex = 0;
+    if (chunk != 0) {
+        int look = (int)chunk - 1;
+        while (true) {
+            const int idx = look - lane;
+            unsigned long long st = S2_PREFIX;
+            if (idx >= 0) {
+                st = ld_vol(status + idx);
+                while ((st & S2_FLAGS) == 0) st = ld_vol(status + idx);
+            }
+            const unsigned pm = __ballot_sync(FULL, (st & S2_FLAGS) == S2_PREFIX);
+            const int first = pm ? (__ffs(pm) - 1) : 32;
+            unsigned long long ct = (lane <= first) ? (st & S2_COUNT) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(FULL, ct, o);
+            ex += ct;
+            if (pm) break;
+            look -= 32;
+        }
+        if (lane == 0) st_vol(status + chunk, S2_PREFIX | (ex + blk_total));
+    }
+    return ex;
+}
+
+struct CullGauss {
+    float ux, uy, A, B, C, inv_a, c2, dy_ext, dy_star;  // c2 = c, dy_ext = sqrt(A c / det), dy_star = (B / C) sqrt(c C / det)
+    bool ok;                                            // false: not positive definite / NaN -> never cull
+};
+
+__device__ __forceinline__ CullGauss cull_setup(float4 r0, float C, float reach_x, float reach_y) {
+    CullGauss g;
+    g.ux = r0.x;
+    g.uy = r0.y;
+    g.A = r0.z;
+    g.B = r0.w;
+    g.C = C;
+    const float det = g.A * g.C - g.B * g.B;
+    g.ok = g.A > 0.0f && g.C > 0.0f && det > 0.0f;
+    // bound on the fp32 rounding error of render.comp:66 anywhere inside the AABB (|dx| <= reach_x, |dy| <= reach_y)
+    const float mag = 0.5f * (g.A * reach_x * reach_x + g.C * reach_y * reach_y) + fabsf(g.B) * reach_x * reach_y;
+    const float margin = 0.03f + 4e-6f * mag;
+    g.c2 = 2.0f * (-POWER_CUT + margin);
+    g.inv_a = 1.0f / g.A;
+    g.dy_ext = sqrtf(g.A * g.c2 / det) * 1.0001f + 1e-3f;
+    g.dy_star = (g.B / g.C) * sqrtf(g.c2 * g.C / det);
+    return g;
+}
+
+// Tile span [xa, xb] (inclusive, clipped to [x0, x1]) of tile row ty that the ellipse may touch; xa > xb = empty.
+__device__ __forceinline__ void cull_row_span(const CullGauss& g, uint32_t ty, int x0, int x1, int& xa, int& xb) {
+    if (!g.ok) {
+        xa = x0;
+        xb = x1;
+        return;
+    }
+    // d = uv - pixel; the row's pixel centres are y in [16 ty, 16 ty + 15]
+    const float dy_lo = g.uy - (float)(ty * GSB_TILE + (GSB_TILE - 1)), dy_hi = g.uy - (float)(ty * GSB_TILE);
+    const float lo = fmaxf(dy_lo, -g.dy_ext), hi = fminf(dy_hi, g.dy_ext);
+    if (!(lo <= hi)) {  // the slab misses the ellipse (NaN -> keep everything)
+        if (lo > hi) {
+            xa = 1;
+            xb = 0;
+        } else {
+            xa = x0;
+            xb = x1;
+        }
+        return;
+    }
+    // dx range: dx = (-B dy -+ sqrt(A c - det dy^2)) / A.  max at dy = -dy_star, min at dy = +dy_star (clamped)
+    const float det = g.A * g.C - g.B * g.B;
+    const float dy1 = fminf(fmaxf(-g.dy_star, lo), hi), dy2 = fminf(fmaxf(g.dy_star, lo), hi);
+    const float dx_max = (-g.B * dy1 + sqrtf(fmaxf(0.0f, g.A * g.c2 - det * dy1 * dy1))) * g.inv_a;
+    const float dx_min = (-g.B * dy2 - sqrtf(fmaxf(0.0f, g.A * g.c2 - det * dy2 * dy2))) * g.inv_a;
+    // pixel x = ux - dx in [ux - dx_max, ux - dx_min], widened by a slack that dwarfs the rounding of this formula
+    const float slack = 0.01f + 1e-4f * (fabsf(dx_max) + fabsf(dx_min));
+    const float px_lo = g.ux - dx_max - slack, px_hi = g.ux - dx_min + slack;
+    // tile tx holds pixel centres [16 tx, 16 tx + 15]: keep tx with 16 tx <= px_hi and 16 tx + 15 >= px_lo
+    const int ta = (int)ceilf((px_lo - (float)(GSB_TILE - 1)) * (1.0f / GSB_TILE));
+    const int tb = (int)floorf(px_hi * (1.0f / GSB_TILE));
+    xa = max(x0, ta);
+    xb = min(x1, tb);
+    if (!(px_lo <= px_hi)) {  // NaN safety
+        xa = x0;
+        xb = x1;
+    }
+}
+
+__global__ void __launch_bounds__(PRE_THREADS) k_emit_cull(const __grid_constant__ EmitParams P) {
+    __shared__ uint32_t s_chunk;
+    __shared__ uint32_t s_wnt[PRE_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_nbig;
+    __shared__ uint32_t s_big[PRE_THREADS];
+    __shared__ uint4 s_info[PRE_THREADS];  // x0 | y0 << 16, w | h << 16, local offset, compact id (big Gaussians)
+    __shared__ uint32_t s_key[EMIT_WIN];
+    __shared__ uint32_t s_val[EMIT_WIN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nv = P.ctl->num_visible;
+    const uint32_t num_chunks = (nv + PRE_THREADS - 1) / PRE_THREADS;
+    const uint32_t tiles_x = P.tiles_x;
+
+    while (true) {
+        if (tid == 0) {
+            s_chunk = atomicAdd(&P.ctl->emit_ticket, 1u);
+            s_nbig = 0;
+        }
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= num_chunks) break;
+        const uint32_t j = chunk * PRE_THREADS + tid;
+
+        uint32_t nt = 0, cand = 0, cid = 0, xy = 0, wh = 0;
+        CullGauss g{};
+        if (j < nv) {
+            cid = __ldg(P.sorted_cid + j);
+            const uint2 inf = __ldg(P.einfo + cid);
+            xy = inf.x;
+            wh = inf.y;
+            cand = (wh & 0xffffu) * (wh >> 16);
+            nt = cand;
+            if (cand != 0 && cand <= EMIT_BIG) {
+                const float4 r0 = __ldg(P.recs + (size_t)cid * 3);
+                const float cc = __ldg(reinterpret_cast<const float*>(P.recs + (size_t)cid * 3 + 1));
+                const float radius = __ldg(reinterpret_cast<const float*>(P.recs + (size_t)cid * 3 + 2) + 2);
+                const float reach = radius + 32.0f;  // |uv - pixel| inside the AABB's tiles
+                g = cull_setup(r0, cc, reach, reach);
+                const int gx0 = (int)(xy & 0xffffu), gx1 = gx0 + (int)(wh & 0xffffu) - 1;
+                nt = 0;
+                for (uint32_t r = 0; r < (wh >> 16); r++) {
+                    int xa, xb;
+                    cull_row_span(g, (xy >> 16) + r, gx0, gx1, xa, xb);
+                    nt += (uint32_t)max(0, xb - xa + 1);
+                }
+            }
+        }
+        // ---- block scan of the (culled) tile counts ----
+        uint32_t nt_incl = nt, cand_sum = cand;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, nt_incl, o);
+            if (lane >= o) nt_incl += t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand_sum += __shfl_xor_sync(FULL, cand_sum, o);
+        if (lane == 31) s_wnt[warp] = nt_incl;
+        if (lane == 0 && cand_sum) atomicAdd(&P.ctl->candidates_total, (unsigned long long)cand_sum);
+        __syncthreads();
+        uint32_t nt_before = 0, blk_nt = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; w++) {
+            const uint32_t b = s_wnt[w];
+            if (w < warp) nt_before += b;
+            blk_nt += b;
+        }
+        const uint32_t off = nt_before + (nt_incl - nt);
+        if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
+        if (cand > EMIT_BIG) {
+            s_info[tid] = make_uint4(xy, wh, off, cid);
+            s_big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
+        }
+        __syncthreads();
+        const uint32_t nbig = s_nbig;
+        unsigned long long base = 0;
+
+        for (uint32_t w0 = 0; w0 == 0 || w0 < blk_nt; w0 += EMIT_WIN) {  // at least once: the look-back lives inside
+            const uint32_t w1 = min(blk_nt, w0 + (uint32_t)EMIT_WIN);
+            if (nt != 0 && cand <= EMIT_BIG && off < w1 && off + nt > w0) {  // small Gaussians: own surviving tiles, row-major
+                const int gx0 = (int)(xy & 0xffffu), gx1 = gx0 + (int)(wh & 0xffffu) - 1;
+                uint32_t o = off;
+                for (uint32_t r = 0; r < (wh >> 16); r++) {
+                    const uint32_t ty = (xy >> 16) + r;
+                    int xa, xb;
+                    cull_row_span(g, ty, gx0, gx1, xa, xb);
+                    for (int x = xa; x <= xb; x++, o++) {
+                        if (o >= w0 && o < w1) {
+                            s_key[o - w0] = (uint32_t)x + ty * tiles_x;
+                            s_val[o - w0] = cid;
+                        }
+                    }
+                }
+            }
+            for (uint32_t b = 0; b < nbig; b++) {  // big Gaussians: whole AABB, expanded by the whole block
+                const uint4 inf = s_info[s_big[b]];
+                const uint32_t bh = inf.y >> 16, bnt = (inf.y & 0xffffu) * bh;
+                const uint32_t lo = max(inf.z, w0), hi = min(inf.z + bnt, w1);
+                for (uint32_t o = lo + tid; o < hi; o += PRE_THREADS) {
+                    const uint32_t k = o - inf.z, q = k / bh, r = k - q * bh;
+                    s_key[o - w0] = ((inf.x & 0xffffu) + q) + ((inf.x >> 16) + r) * tiles_x;
+                    s_val[o - w0] = inf.w;
+                }
+            }
+            if (w0 == 0 && warp == 0) {  // look-back after the first fill: the predecessors' latency overlaps local work
+                const unsigned long long ex = emit_lookback(P.status, chunk, lane, blk_nt);
+                if (lane == 0) {
+                    s_base = ex;
+                    if (chunk == num_chunks - 1) {
+                        const unsigned long long total = ex + blk_nt;
+                        P.ctl->instances_total = total;
+                        P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
+                        P.ctl->overflow = total > P.capacity ? 1u : 0u;
+                    }
+                }
+            }
+            __syncthreads();
+            if (w0 == 0) base = s_base;
+            for (uint32_t i = tid; i < w1 - w0; i += PRE_THREADS) {  // coalesced copy-out
+                const unsigned long long slot = base + w0 + i;
+                if (slot < P.capacity) {
+                    P.keys[slot] = s_key[i];
+                    P.vals[slot] = s_val[i];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_project(const ProjectParams& p, bool debug, cudaStream_t s) {
@@ -451,7 +690,8 @@ cudaError_t launch_emit(const EmitParams& p, cudaStream_t s) {
     const uint32_t cap = (uint32_t)p.num_sms * 8;  // ticket loop: any grid size is correct
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
-    k_emit<<<blocks, PRE_THREADS, 0, s>>>(p);
+    if (p.cull) k_emit_cull<<<blocks, PRE_THREADS, 0, s>>>(p);
+    else k_emit<<<blocks, PRE_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -37,7 +37,7 @@ ALL_ROWS = 0xFFFFFFFF
 
 EXPORTED_SYMBOLS = [  # every symbol include/gs_b200.h declares
     "gsb_abi_version", "gsb_device_count", "gsb_create", "gsb_destroy", "gsb_last_error",
-    "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers",
+    "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers", "gsb_set_tile_cull",
     "gsb_reserve_instances", "gsb_render", "gsb_render_async", "gsb_get_stats", "gsb_debug_size",
     "gsb_debug_download", "gsb_sort_pairs",
 ]
@@ -60,7 +60,7 @@ assert C.sizeof(Uniforms) == 160
 
 
 class Stats(C.Structure):
-    _fields_ = [("num_gaussians", C.c_uint64), ("num_visible", C.c_uint64), ("num_instances", C.c_uint64),
+    _fields_ = [("num_gaussians", C.c_uint64), ("num_visible", C.c_uint64), ("num_instances", C.c_uint64), ("num_instances_aabb", C.c_uint64),
                 ("blend_consumed", C.c_uint64), ("instance_capacity", C.c_uint64), ("sort_passes", C.c_uint32),
                 ("regrow_count", C.c_uint32), ("preprocess_ms", C.c_float), ("prefix_sum_ms", C.c_float),
                 ("preprocess_sort_ms", C.c_float), ("sort_ms", C.c_float), ("tile_boundary_ms", C.c_float),
@@ -98,6 +98,7 @@ lib.gsb_scene_size.restype = C.c_uint64
 lib.gsb_set_mode.argtypes = [_vp, C.c_int]
 lib.gsb_set_debug.argtypes = [_vp, C.c_int]
 lib.gsb_set_timers.argtypes = [_vp, C.c_int]
+lib.gsb_set_tile_cull.argtypes = [_vp, C.c_int]
 lib.gsb_reserve_instances.argtypes = [_vp, C.c_uint64]
 lib.gsb_render.argtypes = [_vp, C.POINTER(Uniforms), C.c_uint32, C.c_uint32, _vp, C.c_size_t, C.c_int, C.c_int, _vp]
 lib.gsb_render_async.argtypes = [_vp, C.POINTER(Uniforms), C.c_uint32, C.c_uint32, _vp, C.c_size_t, C.c_int, _vp]
@@ -278,6 +279,9 @@ class Context:
 
     def set_debug(self, on=True):
         self._ck(lib.gsb_set_debug(self.h, int(on)))
+
+    def set_tile_cull(self, on=True):
+        self._ck(lib.gsb_set_tile_cull(self.h, int(on)))
 
     def set_timers(self, on=True):
         self._ck(lib.gsb_set_timers(self.h, int(on)))

@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tile-cull", type=int, default=1, help="gsb_set_tile_cull (exact instance culling; image bit-identical)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -216,6 +217,7 @@ def main():
 
     ctx = g.Context(local_rank)
     ctx.set_mode(g.MODE_EXACT if args.mode == "exact" else g.MODE_FAST)
+    ctx.set_tile_cull(bool(args.tile_cull))
     ctx.upload(vtx)
     fmt, bpp = g.FORMAT_BGRA8, 4
     band_buf = torch.zeros((rows_per * 16, W, bpp), dtype=torch.uint8, device=dev)
@@ -243,7 +245,7 @@ def main():
         frame(i, sync=True)
 
     # per-stage / per-kernel times (library cudaEvents), sampled on separate untimed frames
-    stage_acc, m_acc, cons_acc, vis_acc, pass_acc = {}, [], [], [], []
+    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc = {}, [], [], [], [], []
     for i in range(NUM_CAMERAS):
         frame(i, sync=True)
         s = ctx.stats()
@@ -253,6 +255,7 @@ def main():
             stage_acc.setdefault(k, []).append(d[k])
         stage_acc.setdefault("sort_pass_ms", []).append(float(np.mean(d["sort_pass_ms"])) if d["sort_pass_ms"] else 0.0)
         m_acc.append(s.num_instances)
+        aabb_acc.append(s.num_instances_aabb)
         cons_acc.append(s.blend_consumed)
         vis_acc.append(s.num_visible)
         passes = s.sort_passes
@@ -326,7 +329,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "note": wl["note"], "n_gaussians": wl["n"], "width": W, "height": H,
-                       "instances_M": M, "visible": NV, "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8",
+                       "instances_M": M, "instances_aabb": float(np.mean(aabb_acc)), "tile_cull": bool(args.tile_cull), "visible": NV, "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8",
                        "cameras": NUM_CAMERAS, "l2": "inputs (1.3 GB scene + 0.4 GB keys) larger than the 126 MB L2; no flush",
                        "parallelism": f"tile-row bands x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 160,

@@ -99,7 +99,9 @@ typedef enum gsb_buffer {
 typedef struct gsb_stats {
     uint64_t num_gaussians;     /* N */
     uint64_t num_visible;       /* N_v: survivors of the three culls */
-    uint64_t num_instances;     /* M  ("instances", Renderer.cpp:540) */
+    uint64_t num_instances;     /* M: (Gaussian, tile) instances emitted and sorted this frame */
+    uint64_t num_instances_aabb; /* AABB instances = the reference's "instances" (Renderer.cpp:540); equals
+                                   num_instances unless gsb_set_tile_cull is on */
     uint64_t blend_consumed;    /* sum over tiles of run entries read before the tile terminated */
     uint64_t instance_capacity; /* current arena capacity in instances */
     uint32_t sort_passes;       /* radix passes of the instance-level (tile id) sort = ceil(log2(T) / 8) */
@@ -134,6 +136,11 @@ uint64_t gsb_scene_size(const gsb_ctx *ctx);
 int gsb_set_mode(gsb_ctx *ctx, gsb_mode mode);
 /* debug != 0: keep every intermediate so gsb_debug_download works (extra HBM traffic). */
 int gsb_set_debug(gsb_ctx *ctx, int debug);
+/* Exact instance culling (default off).  When on, a (Gaussian, tile) instance is dropped at key emission if the
+ * Gaussian provably stays below the shader's own alpha < 1/255 cut on every pixel of the tile: the image is
+ * bit-identical, but M and the key / payload / tile-range buffers are a subset of the reference's
+ * (preprocess_sort.comp:47-58 emits the whole AABB).  Trades a per-candidate test for fewer instances to sort. */
+int gsb_set_tile_cull(gsb_ctx *ctx, int enabled);
 /* per-stage cudaEvent timers (the QueryManager analogue, Renderer.cpp:85-100). Default on. */
 int gsb_set_timers(gsb_ctx *ctx, int enabled);
 /* Pre-size the (tile,depth) instance arena (the reference's sortBufferSizeMultiplier,

@@ -163,3 +163,48 @@ def test_errors(gs):
     with pytest.raises(gs.GsbError) as e:
         gs.Context(9999)
     assert e.value.code == gs.ERR_NO_DEVICE
+
+
+@pytest.mark.parametrize("cam", ["c1", "inside", "odd_size", "wide"])
+def test_tile_cull_keeps_the_image_bit_exact(gs, oracle, ctx, cam):
+    """gsb_set_tile_cull: instances that provably stay below alpha < 1/255 on a whole tile are dropped at emission.
+    The image must stay bit-identical; the sorted (key, payload) list must be an ordered subset of the reference's;
+    every dropped instance must be one that contributes to no pixel of its tile in the oracle."""
+    _, vtx, _ = scenes.c1()
+    u = scenes.camera(cam)
+    ctx.set_mode(gs.MODE_EXACT)
+    ctx.set_debug(True)
+    ctx.set_tile_cull(True)
+    try:
+        ctx.upload(vtx)
+        img = ctx.render(u, gs.FORMAT_RGBA32F)
+        st = ctx.stats()
+        ref = oracle_frame(oracle, vtx, u, 1)
+        assert np.array_equal(img, ref["rgba"])
+        assert st.num_instances_aabb == ref["m"] and st.num_instances <= ref["m"]
+        keys, vals = ctx.download(gs.BUF_KEYS_SORTED), ctx.download(gs.BUF_VALS_SORTED)
+        # ordered subset: (key, val) pairs are unique, so membership + order can be checked via a merge
+        full = {(int(k), int(v)): i for i, (k, v) in enumerate(zip(ref["keys"], ref["vals"]))}
+        pos = np.array([full[(int(k), int(v))] for k, v in zip(keys, vals)], dtype=np.int64)
+        assert np.all(np.diff(pos) > 0)
+        if ref["m"]:
+            # dropped instances: max alpha over the tile's pixels < 1/255 (checked in float64 on a sample)
+            kept = np.zeros(ref["m"], bool)
+            kept[pos] = True
+            dropped = np.nonzero(~kept)[0]
+            rng = np.random.default_rng(1)
+            tiles_x = (u.width + 15) // 16
+            for i in rng.choice(dropped, size=min(300, dropped.size), replace=False) if dropped.size else []:
+                a = ref["attr"][ref["vals"][i]]
+                t = int(ref["keys"][i] >> np.uint64(32))
+                xs = (t % tiles_x) * 16 + np.arange(16)
+                ys = (t // tiles_x) * 16 + np.arange(16)
+                dx, dy = a["uv"][0] - xs[None, :].astype(np.float64), a["uv"][1] - ys[:, None].astype(np.float64)
+                co = a["conic_opacity"].astype(np.float64)
+                power = -0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy
+                assert (co[3] * np.exp(power)).max() < 1.0 / 255.0
+        if cam == "c1":
+            assert st.num_instances < ref["m"]  # the cull actually removes something
+    finally:
+        ctx.set_tile_cull(False)
+        ctx.set_debug(False)
