@@ -49,14 +49,14 @@ __device__ __forceinline__ uint32_t unorm8(float v) {
 }
 
 // Bit w set <=> warp w's 8x4 pixel block may receive a contribution from this Gaussian (gsb_cull.cuh).
-__device__ __forceinline__ uint32_t block_mask(float ux, float uy, float A, float B, float C, float tile_x0, float tile_y0) {
+__device__ __forceinline__ uint32_t block_mask(float ux, float uy, float A, float B, float C, float cut, float tile_x0, float tile_y0) {
     if (!(A > 0.0f) || !(C > 0.0f)) return 0xffu;  // not positive definite / NaN: never cull
     const float inv_a = __frcp_rn(A), inv_c = __frcp_rn(C);
     uint32_t mask = 0;
 #pragma unroll
     for (int w = 0; w < 8; w++) {
         const float x0 = tile_x0 + (float)((w & 1) * 8), y0 = tile_y0 + (float)((w >> 1) * 4);
-        if (rect_may_contribute(ux, uy, A, B, C, inv_a, inv_c, x0, y0, 8.0f, 4.0f)) mask |= 1u << w;
+        if (rect_may_contribute(ux, uy, A, B, C, inv_a, inv_c, x0, y0, 8.0f, 4.0f, cut)) mask |= 1u << w;
     }
     return mask;
 }
@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
     // staged with exact sign / power-of-two scalings so that render.comp:66 needs one multiply less and rounds identically:
     //   -0.5 * ((A dx) dx + (C dy) dy) - (B dx) dy  ==  ((-A/2 dx) dx + (-C/2 dy) dy) + ((-B) dx) dy   (bit for bit)
     __shared__ float4 s_r0[BLEND_THREADS];  // uv.x uv.y -conic.x/2 -conic.y
-    __shared__ float4 s_r1[BLEND_THREADS];  // -conic.z/2 opacity r g
-    __shared__ float s_b[BLEND_THREADS];    // b
+    __shared__ float4 s_r1[BLEND_THREADS];  // -conic.z/2 power_cut(opacity) opacity r
+    __shared__ float2 s_gb[BLEND_THREADS];  // g b
     __shared__ uint32_t s_mask[BLEND_THREADS];
     __shared__ uint32_t s_used;
 
@@ -94,10 +94,11 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
             const uint32_t cid = __ldg(P.vals + base + tid);
             const float4* rec = P.recs + (size_t)cid * 3;
             const float4 a = __ldg(rec), b = __ldg(rec + 1);
+            const float cut = power_cut(b.y);
             s_r0[tid] = make_float4(a.x, a.y, -0.5f * a.z, -a.w);
-            s_r1[tid] = make_float4(-0.5f * b.x, b.y, b.z, b.w);
-            s_b[tid] = __ldg(reinterpret_cast<const float*>(rec + 2));
-            s_mask[tid] = block_mask(a.x, a.y, a.z, a.w, b.x, tile_x0, tile_y0);
+            s_r1[tid] = make_float4(-0.5f * b.x, cut, b.y, b.z);
+            s_gb[tid] = make_float2(b.w, __ldg(reinterpret_cast<const float*>(rec + 2)));
+            s_mask[tid] = block_mask(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
         }
         __syncthreads();
         if (!__all_sync(FULL, done)) {
@@ -114,12 +115,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
                     float alpha;
                     if (MODE == GSB_MODE_EXACT) {
                         const float power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
-                        if (power > 0.0f || power < POWER_CUT) continue;  // :68-70; < POWER_CUT implies alpha < 1/255 (:78); NaN falls through like the shader
-                        alpha = fminf(0.99f, b.y * exp_shared(power));  // :77
+                        if (power > 0.0f || power < b.y) continue;  // :68-70; below the Gaussian's cut alpha < 1/255 (:78); NaN falls through like the shader
+                        alpha = fminf(0.99f, b.z * exp_shared(power));  // :77
                     } else {
                         const float power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
-                        if (power > 0.0f || power < POWER_CUT) continue;
-                        alpha = fminf(0.99f, b.y * __expf(power));
+                        if (power > 0.0f || power < b.y) continue;
+                        alpha = fminf(0.99f, b.z * __expf(power));
                     }
                     if (alpha < 1.0f / 255.0f) continue;      // :78-80
                     const float test_T = T * (1.0f - alpha);  // :82
@@ -129,14 +130,16 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
                         continue;
                     }
                     if (MODE == GSB_MODE_EXACT) {
-                        c0 = c0 + (b.z * alpha) * T;  // :87
-                        c1 = c1 + (b.w * alpha) * T;
-                        c2 = c2 + (s_b[j] * alpha) * T;
+                        const float2 gb = s_gb[j];
+                        c0 = c0 + (b.w * alpha) * T;  // :87
+                        c1 = c1 + (gb.x * alpha) * T;
+                        c2 = c2 + (gb.y * alpha) * T;
                     } else {
+                        const float2 gb = s_gb[j];
                         const float w = alpha * T;
-                        c0 = fmaf(b.z, w, c0);
-                        c1 = fmaf(b.w, w, c1);
-                        c2 = fmaf(s_b[j], w, c2);
+                        c0 = fmaf(b.w, w, c0);
+                        c1 = fmaf(gb.x, w, c1);
+                        c2 = fmaf(gb.y, w, c2);
                     }
                     T = test_T;  // :88
                 }

@@ -16,6 +16,14 @@ namespace gsb {
 
 constexpr float POWER_CUT = -5.55f;  // alpha = opacity * exp(power) <= exp(-5.55) < 1/255 because opacity <= 1
 
+// Per-Gaussian version of the same cut: power < power_cut(opacity) implies opacity * exp(power) < 1/255 in the
+// kernel's arithmetic (the 1e-3 margin dwarfs the error of __logf, of the shared-definition exp and of the final
+// multiply).  Always >= POWER_CUT's companion -log(255) - 1e-3 = -5.5423 since opacity <= 1; clamped to <= 0.
+__device__ __forceinline__ float power_cut(float opacity) {
+    const float c = -__logf(255.0f * opacity) - 1e-3f;  // opacity <= 0 / NaN -> +inf / NaN -> clamped to 0 below
+    return fminf(fmaxf(c, POWER_CUT), 0.0f);
+}
+
 // Minimum over [lo, hi] of the 1-D quadratic  q(t) = a t^2 + 2 b t + c  (a > 0, inv_a ~ 1/a).
 // An inexact minimiser only moves the result by a (t - t*)^2, second order in the rounding error.
 __device__ __forceinline__ float min_quad_1d(float a, float inv_a, float b, float c, float lo, float hi) {
@@ -25,7 +33,7 @@ __device__ __forceinline__ float min_quad_1d(float a, float inv_a, float b, floa
 
 // Pixels [x0, x0 + w - 1] x [y0, y0 + h - 1] (as floats); (ux, uy) = Gaussian centre; A, B, C = conic; A, C > 0.
 __device__ __forceinline__ bool rect_may_contribute(float ux, float uy, float A, float B, float C, float inv_a, float inv_c,
-                                                    float x0, float y0, float w, float h) {
+                                                    float x0, float y0, float w, float h, float cut) {
     // d = uv - pixel
     const float dx_lo = ux - (x0 + (w - 1.0f)), dx_hi = ux - x0, dy_lo = uy - (y0 + (h - 1.0f)), dy_hi = uy - y0;
     float qmin;
@@ -41,7 +49,7 @@ __device__ __forceinline__ bool rect_may_contribute(float ux, float uy, float A,
     const float dxm = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), dym = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
     const float mag = 0.5f * (A * dxm * dxm + C * dym * dym) + fabsf(B) * dxm * dym;  // sum of |terms| of render.comp:66
     const float margin = 0.02f + 2e-6f * mag;  // >= 32 ulp of the largest term: covers both evaluations' rounding
-    return !(-0.5f * qmin < POWER_CUT - margin);  // NaN -> keep
+    return !(-0.5f * qmin < cut - margin);  // NaN -> keep
 }
 
 }  // namespace gsb

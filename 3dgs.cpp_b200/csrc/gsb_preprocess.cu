@@ -486,7 +486,7 @@ struct CullGauss {
     bool ok;                                            // false: not positive definite / NaN -> never cull
 };
 
-__device__ __forceinline__ CullGauss cull_setup(float4 r0, float C, float reach_x, float reach_y) {
+__device__ __forceinline__ CullGauss cull_setup(float4 r0, float C, float opacity, float reach_x, float reach_y) {
     CullGauss g;
     g.ux = r0.x;
     g.uy = r0.y;
@@ -498,7 +498,7 @@ __device__ __forceinline__ CullGauss cull_setup(float4 r0, float C, float reach_
     // bound on the fp32 rounding error of render.comp:66 anywhere inside the AABB (|dx| <= reach_x, |dy| <= reach_y)
     const float mag = 0.5f * (g.A * reach_x * reach_x + g.C * reach_y * reach_y) + fabsf(g.B) * reach_x * reach_y;
     const float margin = 0.03f + 4e-6f * mag;
-    g.c2 = 2.0f * (-POWER_CUT + margin);
+    g.c2 = 2.0f * (-power_cut(opacity) + margin);
     g.inv_a = 1.0f / g.A;
     g.dy_ext = sqrtf(g.A * g.c2 / det) * 1.0001f + 1e-3f;
     g.dy_star = (g.B / g.C) * sqrtf(g.c2 * g.C / det);
@@ -580,10 +580,11 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit_cull(const __grid_constant
             nt = cand;
             if (cand != 0 && cand <= EMIT_BIG) {
                 const float4 r0 = __ldg(P.recs + (size_t)cid * 3);
-                const float cc = __ldg(reinterpret_cast<const float*>(P.recs + (size_t)cid * 3 + 1));
+                const float2 co = __ldg(reinterpret_cast<const float2*>(P.recs + (size_t)cid * 3 + 1));  // conic.z, opacity
+                const float cc = co.x;
                 const float radius = __ldg(reinterpret_cast<const float*>(P.recs + (size_t)cid * 3 + 2) + 2);
                 const float reach = radius + 32.0f;  // |uv - pixel| inside the AABB's tiles
-                g = cull_setup(r0, cc, reach, reach);
+                g = cull_setup(r0, cc, co.y, reach, reach);
                 const int gx0 = (int)(xy & 0xffffu), gx1 = gx0 + (int)(wh & 0xffffu) - 1;
                 nt = 0;
                 for (uint32_t r = 0; r < (wh >> 16); r++) {

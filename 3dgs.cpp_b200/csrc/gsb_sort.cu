@@ -35,7 +35,10 @@ constexpr int HIST_TILE = HIST_THREADS * HIST_IPT;
 constexpr uint32_t LB_AGG = 1u << 30;
 constexpr uint32_t LB_PREFIX = 2u << 30;
 constexpr uint32_t LB_COUNT = (1u << 30) - 1u;
-constexpr int LB_WINDOW = 8;  // predecessors inspected per look-back step (loads in flight)
+#ifndef GSB_LB_WINDOW
+#define GSB_LB_WINDOW 8
+#endif
+constexpr int LB_WINDOW = GSB_LB_WINDOW;  // predecessors inspected per look-back step (loads in flight)
 
 __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
