@@ -1,0 +1,99 @@
+// gs_viewer_headless -- the reference viewer's command line (apps/viewer/main.cpp:12-98) without a window:
+//   gs_viewer_headless [-d DEVICE] [-w WIDTH] [-h HEIGHT] [-v] [--frames N] [--camera x,y,z[,qw,qx,qy,qz]]
+//                      [--fov DEG] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply
+// Loads the .ply through GSScene, renders N frames through Renderer::draw() (B8G8R8A8 like the swapchain),
+// prints the six per-stage timers + `instances` (Renderer.cpp:85-100,540) as one JSON line per run and
+// optionally writes the last frame as a binary PPM.  Environment: VKGS_PHYSICAL_DEVICE like the viewer.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "Renderer.h"
+
+static void usage() {
+    std::puts("usage: gs_viewer_headless [-d device] [-w width] [-h height] [-v] [--frames n] [--camera x,y,z[,qw,qx,qy,qz]]\n"
+              "                          [--fov deg] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply");
+}
+
+int main(int argc, char** argv) {
+    Renderer::Configuration cfg;
+    std::string out_path, scene;
+    uint32_t frames = 1;
+    bool verbose = false, cull = false;
+    float cam[7] = {0, 0, 0, 1, 0, 0, 0};
+    float fov = 45.0f;
+    if (const char* env = std::getenv("VKGS_PHYSICAL_DEVICE")) cfg.physicalDeviceId = static_cast<uint8_t>(std::atoi(env));
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char* {
+            if (i + 1 >= argc) {
+                usage();
+                std::exit(1);
+            }
+            return argv[++i];
+        };
+        if (a == "-d" || a == "--device") cfg.physicalDeviceId = static_cast<uint8_t>(std::atoi(next()));
+        else if (a == "-w" || a == "--width") cfg.width = static_cast<uint32_t>(std::atoi(next()));
+        else if (a == "-h" || a == "--height") cfg.height = static_cast<uint32_t>(std::atoi(next()));
+        else if (a == "-v" || a == "--verbose") verbose = true;
+        else if (a == "--frames") frames = static_cast<uint32_t>(std::atoi(next()));
+        else if (a == "--fov") fov = static_cast<float>(std::atof(next()));
+        else if (a == "--mode") cfg.mode = std::string(next()) == "fast" ? GSB_MODE_FAST : GSB_MODE_EXACT;
+        else if (a == "--cull") cull = true;
+        else if (a == "--out") out_path = next();
+        else if (a == "--camera") {
+            int k = 0;
+            for (char* tok = std::strtok(const_cast<char*>(next()), ","); tok && k < 7; tok = std::strtok(nullptr, ",")) cam[k++] = static_cast<float>(std::atof(tok));
+        } else if (a == "--help") {
+            usage();
+            return 0;
+        } else scene = a;
+    }
+    if (scene.empty()) {
+        usage();
+        return 1;
+    }
+    cfg.scene = scene;
+    try {  // the viewer catches at top level and logs (main.cpp:94-105)
+        Renderer renderer(cfg);
+        const auto t0 = std::chrono::steady_clock::now();
+        renderer.initialize();
+        const double load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (cull && gsb_set_tile_cull(renderer.context(), 1) != GSB_OK) throw std::runtime_error("gsb_set_tile_cull failed");
+        renderer.camera.position = {cam[0], cam[1], cam[2]};
+        renderer.camera.rotation = {cam[3], cam[4], cam[5], cam[6]};
+        renderer.camera.fov = fov;
+        if (verbose) std::fprintf(stderr, "loaded %llu Gaussians in %.1f ms\n", (unsigned long long)renderer.getScene()->getNumVertices(), load_ms);
+        const auto t1 = std::chrono::steady_clock::now();
+        renderer.run(frames);
+        const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+        const gsb_stats s = renderer.retrieveTimestamps();
+        std::printf("{\"scene\": \"%s\", \"gaussians\": %llu, \"width\": %u, \"height\": %u, \"frames\": %u, \"fps_wall\": %.2f, "
+                    "\"instances\": %llu, \"instances_aabb\": %llu, \"visible\": %llu, \"preprocess_ms\": %.4f, \"prefix_sum_ms\": %.4f, "
+                    "\"preprocess_sort_ms\": %.4f, \"sort_ms\": %.4f, \"tile_boundary_ms\": %.4f, \"render_ms\": %.4f, \"frame_ms\": %.4f}\n",
+                    scene.c_str(), (unsigned long long)s.num_gaussians, cfg.width, cfg.height, frames, 1000.0 * frames / wall_ms,
+                    (unsigned long long)s.num_instances, (unsigned long long)s.num_instances_aabb, (unsigned long long)s.num_visible,
+                    s.preprocess_ms, s.prefix_sum_ms, s.preprocess_sort_ms, s.sort_ms, s.tile_boundary_ms, s.render_ms, s.frame_ms);
+        if (!out_path.empty()) {
+            const auto& px = renderer.frame();  // B8G8R8A8
+            std::ofstream f(out_path, std::ios::binary);
+            f << "P6\n" << cfg.width << " " << cfg.height << "\n255\n";
+            std::vector<unsigned char> rgb(static_cast<size_t>(cfg.width) * cfg.height * 3);
+            for (size_t p = 0; p < static_cast<size_t>(cfg.width) * cfg.height; p++) {
+                rgb[p * 3 + 0] = px[p * 4 + 2];
+                rgb[p * 3 + 1] = px[p * 4 + 1];
+                rgb[p * 3 + 2] = px[p * 4 + 0];
+            }
+            f.write(reinterpret_cast<const char*>(rgb.data()), static_cast<std::streamsize>(rgb.size()));
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "critical: %s\n", e.what());
+        return 2;
+    }
+    return 0;
+}
