@@ -61,14 +61,18 @@ __device__ __forceinline__ uint32_t block_mask(float ux, float uy, float A, floa
     return mask;
 }
 
+// one staged record (48 B): three 16-B slots so the inner loop addresses it with one byte offset
+struct __align__(16) StagedRec {
+    float4 r0;  // uv.x uv.y -conic.x/2 -conic.y      (exact sign / power-of-two scalings: render.comp:66 becomes
+    float4 r1;  // -conic.z/2 power_cut opacity r       ((-A/2 dx) dx + (-C/2 dy) dy) + ((-B) dx) dy, bit for bit)
+    float4 r2;  // g b - -
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__ BlendParams P) {
-    // staged with exact sign / power-of-two scalings so that render.comp:66 needs one multiply less and rounds identically:
-    //   -0.5 * ((A dx) dx + (C dy) dy) - (B dx) dy  ==  ((-A/2 dx) dx + (-C/2 dy) dy) + ((-B) dx) dy   (bit for bit)
-    __shared__ float4 s_r0[BLEND_THREADS];  // uv.x uv.y -conic.x/2 -conic.y
-    __shared__ float4 s_r1[BLEND_THREADS];  // -conic.z/2 power_cut(opacity) opacity r
-    __shared__ float2 s_gb[BLEND_THREADS];  // g b
+    __shared__ StagedRec s_rec[BLEND_THREADS];
     __shared__ uint32_t s_mask[BLEND_THREADS];
+    __shared__ uint16_t s_list[BLEND_THREADS / 32][BLEND_THREADS];  // per warp: byte offsets of the records it must visit
     __shared__ uint32_t s_used;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -87,6 +91,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
     float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
     bool done = !inside;
     uint32_t used = 0;
+    const unsigned char* rec_base = reinterpret_cast<const unsigned char*>(s_rec);
 
     for (uint32_t base = range.x; base < range.y; base += BLEND_THREADS) {
         const uint32_t cnt = min((uint32_t)BLEND_THREADS, range.y - base);
@@ -95,55 +100,58 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
             const float4* rec = P.recs + (size_t)cid * 3;
             const float4 a = __ldg(rec), b = __ldg(rec + 1);
             const float cut = power_cut(b.y);
-            s_r0[tid] = make_float4(a.x, a.y, -0.5f * a.z, -a.w);
-            s_r1[tid] = make_float4(-0.5f * b.x, cut, b.y, b.z);
-            s_gb[tid] = make_float2(b.w, __ldg(reinterpret_cast<const float*>(rec + 2)));
+            s_rec[tid].r0 = make_float4(a.x, a.y, -0.5f * a.z, -a.w);
+            s_rec[tid].r1 = make_float4(-0.5f * b.x, cut, b.y, b.z);
+            s_rec[tid].r2 = make_float4(b.w, __ldg(reinterpret_cast<const float*>(rec + 2)), 0.f, 0.f);
             s_mask[tid] = block_mask(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
         }
         __syncthreads();
         if (!__all_sync(FULL, done)) {
+            // compact this warp's survivors of the batch into a list of byte offsets (one ballot per 32 records)
+            uint32_t n = 0;
             for (uint32_t c = 0; c < cnt; c += 32) {
-                const uint32_t mk = (c + lane < cnt) ? s_mask[c + lane] : 0u;
-                unsigned bits = __ballot_sync(FULL, (mk >> warp) & 1u);
-                while (bits) {
-                    const uint32_t j = c + (uint32_t)__ffs(bits) - 1u;
-                    bits &= bits - 1u;
-                    if (done) continue;
-                    const float4 a = s_r0[j];
-                    const float4 b = s_r1[j];
-                    const float dx = a.x - fx, dy = a.y - fy;  // :64
-                    float alpha;
-                    if (MODE == GSB_MODE_EXACT) {
-                        const float power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
-                        if (power > 0.0f || power < b.y) continue;  // :68-70; below the Gaussian's cut alpha < 1/255 (:78); NaN falls through like the shader
-                        alpha = fminf(0.99f, b.z * exp_shared(power));  // :77
-                    } else {
-                        const float power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
-                        if (power > 0.0f || power < b.y) continue;
-                        alpha = fminf(0.99f, b.z * __expf(power));
-                    }
-                    if (alpha < 1.0f / 255.0f) continue;      // :78-80
-                    const float test_T = T * (1.0f - alpha);  // :82
-                    if (test_T < 0.0001f) {                   // :83-85
-                        done = true;
-                        used = base - range.x + j + 1;
-                        continue;
-                    }
-                    if (MODE == GSB_MODE_EXACT) {
-                        const float2 gb = s_gb[j];
-                        c0 = c0 + (b.w * alpha) * T;  // :87
-                        c1 = c1 + (gb.x * alpha) * T;
-                        c2 = c2 + (gb.y * alpha) * T;
-                    } else {
-                        const float2 gb = s_gb[j];
-                        const float w = alpha * T;
-                        c0 = fmaf(b.w, w, c0);
-                        c1 = fmaf(gb.x, w, c1);
-                        c2 = fmaf(gb.y, w, c2);
-                    }
-                    T = test_T;  // :88
+                const bool mine = (c + lane < cnt) && ((s_mask[c + lane] >> warp) & 1u);
+                const unsigned bits = __ballot_sync(FULL, mine);
+                if (mine) s_list[warp][n + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((c + lane) * sizeof(StagedRec));
+                n += __popc(bits);
+            }
+            __syncwarp();
+            for (uint32_t k = 0; k < n; k++) {
+                if ((k & 15u) == 15u && __all_sync(FULL, done)) break;
+                const uint32_t off = s_list[warp][k];
+                if (done) continue;
+                const float4 a = *reinterpret_cast<const float4*>(rec_base + off);
+                const float4 b = *reinterpret_cast<const float4*>(rec_base + off + 16);
+                const float dx = a.x - fx, dy = a.y - fy;  // :64
+                float alpha;
+                if (MODE == GSB_MODE_EXACT) {
+                    const float power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
+                    if (power > 0.0f || power < b.y) continue;  // :68-70; below the Gaussian's cut alpha < 1/255 (:78); NaN falls through like the shader
+                    alpha = fminf(0.99f, b.z * exp_shared(power));  // :77
+                } else {
+                    const float power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
+                    if (power > 0.0f || power < b.y) continue;
+                    alpha = fminf(0.99f, b.z * __expf(power));
                 }
-                if (__all_sync(FULL, done)) break;
+                if (alpha < 1.0f / 255.0f) continue;      // :78-80
+                const float test_T = T * (1.0f - alpha);  // :82
+                if (test_T < 0.0001f) {                   // :83-85
+                    done = true;
+                    used = base - range.x + off / (uint32_t)sizeof(StagedRec) + 1;
+                    continue;
+                }
+                const float2 gb = *reinterpret_cast<const float2*>(rec_base + off + 32);
+                if (MODE == GSB_MODE_EXACT) {
+                    c0 = c0 + (b.w * alpha) * T;  // :87
+                    c1 = c1 + (gb.x * alpha) * T;
+                    c2 = c2 + (gb.y * alpha) * T;
+                } else {
+                    const float w = alpha * T;
+                    c0 = fmaf(b.w, w, c0);
+                    c1 = fmaf(gb.x, w, c1);
+                    c2 = fmaf(gb.y, w, c2);
+                }
+                T = test_T;  // :88
             }
             if (!done) used = base - range.x + cnt;
         }
