@@ -227,6 +227,7 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     sa.sc = &ctx->ctl->sort_depth;
     sa.num_sms = ctx->num_sms;
     sa.events = nullptr;
+    sa.ranges = nullptr;
     uint32_t depth_passes = 0;
     CK(launch_sort(sa, &depth_passes, stream));
     const int fin_a = depth_passes & 1;
@@ -279,12 +280,14 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     sp.sc = &ctx->ctl->sort_tile;
     sp.num_sms = ctx->num_sms;
     sp.events = ctx->timers ? ctx->ev_sort : nullptr;
+    sp.ranges = ctx->ranges;  // the last pass writes the tile ranges (tile_boundary.comp fused)
+    CK(launch_ranges_init(ctx->ranges, T, stream));
     uint32_t passes = 0;
     CK(launch_sort(sp, &passes, stream));
     const int fin = passes & 1;
     if (ctx->timers) CK(cudaEventRecord(ctx->ev[4], stream));
 
-    CK(launch_tile_ranges(ctx->keys[fin], sp.d_m, sp.m_hint, ctx->ranges, T, ctx->num_sms, stream));
+    if (passes == 0) CK(launch_ranges_single_tile(sp.d_m, ctx->ranges, stream));  // one tile: nothing to sort
     if (ctx->timers) CK(cudaEventRecord(ctx->ev[5], stream));
 
     BlendParams bp{};
@@ -776,9 +779,15 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
             }
             return GSB_OK;
         }
-        case GSB_BUF_TILE_BOUNDARY:
+        case GSB_BUF_TILE_BOUNDARY: {  // device encoding (start, ~end), untouched = all ones -> the reference's (start, end) / (0, 0)
             CK(cudaMemcpy(dst, ctx->ranges, need, cudaMemcpyDeviceToHost));
+            uint32_t* o = static_cast<uint32_t*>(dst);
+            for (size_t t = 0; t < need / 8; t++) {
+                if (o[2 * t] == 0xffffffffu) o[2 * t] = o[2 * t + 1] = 0u;
+                else o[2 * t + 1] = ~o[2 * t + 1];
+            }
             return GSB_OK;
+        }
         default: return fail(ctx, GSB_ERR_INVALID, "unknown buffer id");
     }
 }
@@ -816,6 +825,7 @@ int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
     sp.sc = &ctx->ctl->sort_tile;
     sp.num_sms = ctx->num_sms;
     sp.events = nullptr;
+    sp.ranges = nullptr;
     uint32_t passes = 0;
     if (e == cudaSuccess) e = launch_sort(sp, &passes, s);
     if (e == cudaSuccess && (passes & 1)) {  // odd pass count: bring the result back to the "Even" buffers

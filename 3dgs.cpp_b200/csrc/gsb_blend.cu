@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % P.tiles_x;
     const uint32_t ty = P.tile_row_begin + blockIdx.x / P.tiles_x;
-    const uint2 range = P.ranges[ty * P.tiles_x + tx];  // render.comp:43-44
+    uint2 range = P.ranges[ty * P.tiles_x + tx];  // render.comp:43-44; stored as (start, ~end), empty = all ones
+    range.y = ~range.y;
     // warp w owns the 8x4 pixel block at (8 * (w & 1), 4 * (w >> 1)) of the tile
     const uint32_t px = tx * GSB_TILE + (warp & 1) * 8 + (lane & 7);
     const uint32_t py = ty * GSB_TILE + (warp >> 1) * 4 + (lane >> 3);

@@ -12,7 +12,7 @@
 //           einfo[Nv]  uint2 (x0 | y0 << 16, w | h << 16) tile AABB of the survivor
 //           dkeys[2][Nv] u32 bits(depth), dvals[2][Nv] u32 compact id      -- Gaussian-level sort
 //           keys[2][cap] u32 tile id,     vals[2][cap] u32 compact id      -- instance-level sort
-//           ranges[T] uint2 (start, end) per tile
+//           ranges[T] uint2 (start, ~end) per tile; (0xFFFFFFFF, 0xFFFFFFFF) = empty
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -99,13 +99,14 @@ struct SortParams {
     SortCtl* sc;               // must be zero on entry
     int num_sms;
     cudaEvent_t* events;       // optional: events[0] after the histogram, events[1 + p] after pass p
+    uint2* ranges;             // optional (u32 keys): the last pass also produces the tile ranges (start, ~end)
 };
 // Returns the number of passes P via *passes; sorted data ends in keys[P & 1].
 cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s);
 uint32_t sort_tile_items();
 
-cudaError_t launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_m, uint32_t m_hint, uint2* ranges,
-                               uint32_t num_tiles, int num_sms, cudaStream_t s);
+cudaError_t launch_ranges_init(uint2* ranges, uint32_t num_tiles, cudaStream_t s);  // (0xFFFFFFFF, 0xFFFFFFFF) = empty
+cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaStream_t s);
 
 struct BlendParams {
     const float4* recs;

@@ -202,7 +202,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
     k_onesweep_pass(const KeyT* __restrict__ kin, const uint32_t* __restrict__ vin, KeyT* __restrict__ kout,
                     uint32_t* __restrict__ vout, const uint32_t* __restrict__ d_m, SortCtl* sc, int pass,
-                    unsigned long long* status, uint32_t status_tiles, uint32_t epoch) {
+                    unsigned long long* status, uint32_t status_tiles, uint32_t epoch, uint2* __restrict__ ranges) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PassSmem<KeyT>& S = *reinterpret_cast<PassSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -379,6 +379,24 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
                     vout[g[it]] = v[it];
                 }
             }
+            // Tile ranges fused into the LAST pass (tile_boundary.comp:22-50): inside one digit bin the tile keeps its
+            // input order, which is sorted by the lower digits, so equal keys are adjacent in the shared-memory
+            // buffer and land on consecutive global positions.  Every maximal run reports its first position with
+            // atomicMin on ranges[key].x and its end with atomicMin on ranges[key].y = ~end (both fields start at
+            // 0xFFFFFFFF); runs split across tiles merge by the min.
+            if (ranges != nullptr) {
+                if constexpr (sizeof(KeyT) == 4) {
+#pragma unroll
+                    for (int it = 0; it < SORT_IPT; it++) {
+                        const uint32_t idx = (uint32_t)(it * SORT_THREADS + tid);
+                        if (idx < valid) {
+                            const uint32_t key = (uint32_t)k[it];
+                            if (idx == 0 || (uint32_t)sk[idx - 1] != key) atomicMin(&ranges[key].x, (uint32_t)g[it]);
+                            if (idx == valid - 1 || (uint32_t)sk[idx + 1] != key) atomicMin(&ranges[key].y, ~((uint32_t)g[it] + 1u));
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();  // buffer `cur` may now be refilled by TMA
         cur ^= 1;
@@ -432,7 +450,8 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
     for (uint32_t pass = 0; pass < P; pass++) {
         const int src = pass & 1, dst = src ^ 1;
         k_onesweep_pass<KeyT><<<blocks, SORT_THREADS, smem, s>>>(keys[src], p.vals[src], keys[dst], p.vals[dst], p.d_m, p.sc,
-                                                                 (int)pass, p.status, p.status_tiles, p.epoch_base + pass);
+                                                                 (int)pass, p.status, p.status_tiles, p.epoch_base + pass,
+                                                                 pass + 1 == P ? p.ranges : nullptr);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (p.events && (e = cudaEventRecord(p.events[1 + pass], s)) != cudaSuccess) return e;
@@ -455,38 +474,23 @@ cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------
 // Tile ranges (replaces fillBuffer(0) + tile_boundary.comp:22-50, Renderer.cpp:633-652).
-// The sorted keys here are the 32-bit tile ids (the high half of the reference's 64-bit key).
+// Encoding: ranges[t] = (start, ~end), untouched = (0xFFFFFFFF, 0xFFFFFFFF) = empty.  They are produced by the
+// last Onesweep pass of the instance sort (see k_onesweep_pass); this file only provides the 0xFF fill and the
+// degenerate case of a single tile (no tile-id bits to sort, hence no pass).
 // ------------------------------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(256) k_tile_ranges(const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ d_m,
-                                                     uint2* __restrict__ ranges) {
+__global__ void k_ranges_single_tile(const uint32_t* __restrict__ d_m, uint2* __restrict__ ranges) {
     const uint32_t m = *d_m;
-    uint32_t* r = reinterpret_cast<uint32_t*>(ranges);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        const uint32_t key = __ldg(tile_keys + i);
-        if (i == 0) {
-            r[key * 2] = 0;
-        } else {
-            const uint32_t prev = __ldg(tile_keys + i - 1);
-            if (key != prev) {
-                r[key * 2] = i;
-                r[prev * 2 + 1] = i;
-            }
-        }
-        if (i == m - 1) r[key * 2 + 1] = m;
-    }
+    if (m) ranges[0] = make_uint2(0u, ~m);
 }
 }  // namespace
 
-cudaError_t launch_tile_ranges(const uint32_t* tile_keys, const uint32_t* d_m, uint32_t m_hint, uint2* ranges,
-                               uint32_t num_tiles, int num_sms, cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), s);
-    if (e != cudaSuccess) return e;
-    uint32_t blocks = (m_hint + 255) / 256;
-    const uint32_t cap = (uint32_t)num_sms * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks == 0) blocks = 1;
-    k_tile_ranges<<<blocks, 256, 0, s>>>(tile_keys, d_m, ranges);
+cudaError_t launch_ranges_init(uint2* ranges, uint32_t num_tiles, cudaStream_t s) {
+    return cudaMemsetAsync(ranges, 0xFF, (size_t)num_tiles * sizeof(uint2), s);
+}
+
+cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaStream_t s) {
+    k_ranges_single_tile<<<1, 1, 0, s>>>(d_m, ranges);
     return cudaGetLastError();
 }
 

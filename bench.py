@@ -335,13 +335,12 @@ def main():
             kd: nv * (4 + 16 * 4),                                     # histogram read + 4 x (8 B read + 8 B written)
             "k_emit": nv * (4 + 8) + 8 * M,                            # sorted ids + AABBs in, (tile id, payload) out
             "k_sort_hist": 4 * M,
-            "k_onesweep_pass": 16 * M,                                 # 8 B read + 8 B written per (tile id, payload) pair
-            "k_tile_ranges": 4 * M + 8 * T_tiles,
+            "k_onesweep_pass": 16 * M + 4 * T_tiles,                   # 8 B read + 8 B written per (tile id, payload) pair (+ tile ranges, last pass)
             "k_blend": CONS * (4 + 36) + (nrows if world == 1 else H) * W * bpp,
         }
         dur = {"k_project": stage["preprocess_ms"], kd: stage["sort_depth_ms"], "k_emit": stage["preprocess_sort_ms"],
                "k_sort_hist": stage["sort_hist_ms"], "k_onesweep_pass": stage["sort_pass_ms"],
-               "k_tile_ranges": stage["tile_boundary_ms"], "k_blend": stage["render_ms"]}
+               "k_blend": stage["render_ms"]}
         share = dict(dur)
         share["k_onesweep_pass"] = stage["sort_pass_ms"] * passes
         kern = {k: {"ms_per_launch": dur[k], "launches_per_step": passes if k == "k_onesweep_pass" else (5 if k == kd else 1),
@@ -364,7 +363,7 @@ def main():
                     "d2h_bytes_per_step": int(nrows * W * bpp) + 64,
                     "api": "gsb_render_async(host UBO) + cudaMemcpyAsync of every BGRA8 frame to pinned host memory, double buffered",
                     "sync_value": e2e_sync_fps, "sync_api": "gsb_render(host UBO -> host BGRA8), one blocking call per frame"},
-            "gpu_launches": int((10 + passes) * args.steps),  # project, hist+4 passes (depth), emit, hist+P passes (tile), ranges, blend
+            "gpu_launches": int((9 + passes) * args.steps),  # project, hist+4 passes (depth), emit, hist+P passes (tile; the last one also writes the tile ranges), blend
             "clocks": clocks,
             "roofline": roof,
             "kernels": kern,
