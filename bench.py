@@ -120,14 +120,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_oracle_sample(wl, vtx, u, budget_s):
+def cpu_oracle_sample(wl, vtx, u, budget_s, cov=None):
     """Times the CPU oracle on a bounded sample: all N Gaussians preprocessed, but only a centred band
     of tile rows sorted + blended; frames/s is extrapolated by rows_total / rows_band for the
     band-proportional stages."""
     sys.path.insert(0, str(ROOT / "oracle"))
     import oracle as o
 
-    cov = o.cov3d(vtx)
+    if cov is None:
+        cov = o.cov3d(vtx)  # GSScene::precomputeCov3D is load-time work, not per frame
     tiles_y = (wl["h"] + 15) // 16
     rows = 1
     mid = tiles_y // 2
@@ -181,8 +182,11 @@ def main():
         total = max(1, args.steps + args.warmup)
         per_step = max(2.0, min(30.0, 150.0 / total))
         vals = []
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import oracle as _o
+        cov = _o.cov3d(vtx)
         for s in range(total):
-            r = cpu_oracle_sample(wl, vtx, cams[s % NUM_CAMERAS], per_step)
+            r = cpu_oracle_sample(wl, vtx, cams[s % NUM_CAMERAS], per_step, cov)
             if s >= args.warmup:
                 vals.append(r)
         fps = float(np.mean([r["fps"] for r in vals]))
