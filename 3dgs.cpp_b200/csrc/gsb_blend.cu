@@ -68,8 +68,11 @@ struct __align__(16) StagedRec {
     float4 r2;  // g b - -
 };
 
+#ifndef GSB_BLEND_MIN_BLOCKS
+#define GSB_BLEND_MIN_BLOCKS 5  // <= 51 registers, 5 CTAs per SM (measured: 0.873 ms; 4 CTAs 0.886, 6 CTAs 0.891, 80 registers 0.972)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(BLEND_THREADS) k_blend(const __grid_constant__ BlendParams P) {
+__global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(const __grid_constant__ BlendParams P) {
     __shared__ StagedRec s_rec[BLEND_THREADS];
     __shared__ uint32_t s_mask[BLEND_THREADS];
     __shared__ uint16_t s_list[BLEND_THREADS / 32][BLEND_THREADS];  // per warp: byte offsets of the records it must visit
