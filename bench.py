@@ -351,8 +351,14 @@ def main():
                     "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (dur[k] * 1e-3) / 1e9 if dur[k] > 0 else None,
                     "share_of_step": share[k] / stage["frame_ms"] if stage["frame_ms"] > 0 else None} for k in alg}
         dom = max(share, key=share.get)
+        traffic = None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+            traffic = tj["dram_bytes_per_launch"].get(dom)
+        except Exception:
+            pass
         roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["achieved_gbs"] / peak if kern[dom]["achieved_gbs"] else None, "traffic": None,
+                "frac": kern[dom]["achieved_gbs"] / peak if kern[dom]["achieved_gbs"] else None, "traffic": traffic,
                 "peak_source": peak_src,
                 "note": "k_blend is FP32/SFU-issue bound (SURVEY 8d): its HBM fraction is reported as required, pair-evals/s beside it"}
         out = {

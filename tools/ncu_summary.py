@@ -57,5 +57,16 @@ s = sum(tot.values()) or 1
 out += ["", "## ncu launch list (gpu__time_duration.sum over the captured launches): share of device time", "", "| kernel | total us | share |", "|---|---|---|"]
 for k, v in tot.items():
     out.append(f"| {k} | {v/1e3:.1f} | {v/s:.3f} |")
+# per-kernel DRAM traffic per launch (largest launch of each kernel) for bench.py's roofline.traffic
+traffic = {}
+for r in data:
+    n = short(r[ix["Kernel Name"]])
+    def mb(key):
+        v, u = float(r[ix[key]]), units[ix[key]]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1e6)
+    b = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+    traffic[n] = max(traffic.get(n, 0), b)
+json.dump({"source": f"{tag}_full.ncu-rep (ncu --set full --clock-control none, one frame)", "dram_bytes_per_launch": traffic},
+          open("profiles/ncu_traffic.json", "w"), indent=1)
 open(f"profiles/{tag}_summary.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out))
