@@ -43,6 +43,23 @@ __device__ __forceinline__ float exp_shared(float x) {
     return __fmul_rn(y, __int_as_float((ni + 127) << 23));
 }
 
+// shared-memory loads by 32-bit shared-window address (one LDS each, immediate offsets, no generic-pointer arithmetic)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ uint32_t unorm8(float v) {
     v = fminf(fmaxf(v, 0.0f), 1.0f);  // NaN -> 0
     return __float2uint_rn(v * 255.0f);
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
     float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
     bool done = !inside;
     uint32_t used = 0;
-    const unsigned char* rec_base = reinterpret_cast<const unsigned char*>(s_rec);
+    const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);  // < 64 KiB: fits the u16 list entries
 
     for (uint32_t base = range.x; base < range.y; base += BLEND_THREADS) {
         const uint32_t cnt = min((uint32_t)BLEND_THREADS, range.y - base);
@@ -111,53 +128,61 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
         }
         __syncthreads();
         if (!__all_sync(FULL, done)) {
-            // compact this warp's survivors of the batch into a list of byte offsets (one ballot per 32 records)
+            // compact this warp's survivors of the batch into a list of shared-memory addresses (one ballot per 32 records)
             uint32_t n = 0;
             for (uint32_t c = 0; c < cnt; c += 32) {
                 const bool mine = (c + lane < cnt) && ((s_mask[c + lane] >> warp) & 1u);
                 const unsigned bits = __ballot_sync(FULL, mine);
-                if (mine) s_list[warp][n + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)((c + lane) * sizeof(StagedRec));
+                if (mine) s_list[warp][n + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)(rec_sh + (c + lane) * sizeof(StagedRec));
                 n += __popc(bits);
             }
             __syncwarp();
-            for (uint32_t k = 0; k < n; k++) {
-                if ((k & 15u) == 15u && __all_sync(FULL, done)) break;
-                const uint32_t off = s_list[warp][k];
-                if (done) continue;
-                const float4 a = *reinterpret_cast<const float4*>(rec_base + off);
-                const float4 b = *reinterpret_cast<const float4*>(rec_base + off + 16);
-                const float dx = a.x - fx, dy = a.y - fy;  // :64
-                float alpha;
-                if (MODE == GSB_MODE_EXACT) {
-                    const float power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
-                    if (power > 0.0f || power < b.y) continue;  // :68-70; below the Gaussian's cut alpha < 1/255 (:78); NaN falls through like the shader
-                    alpha = fminf(0.99f, b.z * exp_shared(power));  // :77
-                } else {
-                    const float power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
-                    if (power > 0.0f || power < b.y) continue;
-                    alpha = fminf(0.99f, b.z * __expf(power));
+            // The walk is branch-free per lane: the shader's `continue`s (render.comp:68-70, :78-80) and `break` (:83-85)
+            // become the predicate `ok`; only the every-16 "whole warp done" test is a (warp-uniform) branch.
+            const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
+            uint32_t fin_k = 0xffffffffu;
+            for (uint32_t k0 = 0; k0 < n; k0 += 16) {
+                if (__all_sync(FULL, done)) break;
+                const uint32_t k1 = min(n, k0 + 16u);
+                for (uint32_t k = k0; k < k1; k++) {
+                    const uint32_t addr = lds_u16(list_sh + 2u * k);
+                    const float4 a = lds_f4(addr);
+                    const float4 b = lds_f4(addr + 16u);
+                    const float2 gb = lds_f2(addr + 32u);
+                    const float dx = a.x - fx, dy = a.y - fy;  // :64
+                    float power, alpha;
+                    if (MODE == GSB_MODE_EXACT) {
+                        power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
+                        alpha = fminf(0.99f, b.z * exp_shared(power));                     // :77
+                    } else {
+                        power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
+                        alpha = fminf(0.99f, b.z * __expf(power));
+                    }
+                    // :68-70 and, below the Gaussian's cut, alpha < 1/255 (:78); a NaN power passes like in the shader
+                    bool ok = !done && !(power > 0.0f || power < b.y) && !(alpha < 1.0f / 255.0f);  // :78-80
+                    const float test_T = T * (1.0f - alpha);  // :82
+                    if (ok && test_T < 0.0001f) {             // :83-85
+                        done = true;
+                        fin_k = k;
+                        ok = false;
+                    }
+                    if (ok) {
+                        if (MODE == GSB_MODE_EXACT) {
+                            c0 = c0 + (b.w * alpha) * T;  // :87
+                            c1 = c1 + (gb.x * alpha) * T;
+                            c2 = c2 + (gb.y * alpha) * T;
+                        } else {
+                            const float w = alpha * T;
+                            c0 = fmaf(b.w, w, c0);
+                            c1 = fmaf(gb.x, w, c1);
+                            c2 = fmaf(gb.y, w, c2);
+                        }
+                        T = test_T;  // :88
+                    }
                 }
-                if (alpha < 1.0f / 255.0f) continue;      // :78-80
-                const float test_T = T * (1.0f - alpha);  // :82
-                if (test_T < 0.0001f) {                   // :83-85
-                    done = true;
-                    used = base - range.x + off / (uint32_t)sizeof(StagedRec) + 1;
-                    continue;
-                }
-                const float2 gb = *reinterpret_cast<const float2*>(rec_base + off + 32);
-                if (MODE == GSB_MODE_EXACT) {
-                    c0 = c0 + (b.w * alpha) * T;  // :87
-                    c1 = c1 + (gb.x * alpha) * T;
-                    c2 = c2 + (gb.y * alpha) * T;
-                } else {
-                    const float w = alpha * T;
-                    c0 = fmaf(b.w, w, c0);
-                    c1 = fmaf(gb.x, w, c1);
-                    c2 = fmaf(gb.y, w, c2);
-                }
-                T = test_T;  // :88
             }
-            if (!done) used = base - range.x + cnt;
+            if (fin_k != 0xffffffffu) used = base - range.x + (s_list[warp][fin_k] - rec_sh) / (uint32_t)sizeof(StagedRec) + 1;
+            else if (!done) used = base - range.x + cnt;
         }
         if (__syncthreads_and(done)) break;
     }
