@@ -65,6 +65,7 @@ struct gsb_ctx {
     cudaEvent_t ev_done = nullptr;
     bool frame_pending = false;
     bool have_frame = false;
+    bool frame_debug = false;  // the last frame ran with gsb_set_debug on (its debug buffers and sorted keys exist)
     uint32_t m_hint = 0;
     uint32_t nv_hint = 0;
     uint32_t regrow_count = 0;
@@ -228,6 +229,7 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     sa.num_sms = ctx->num_sms;
     sa.events = nullptr;
     sa.ranges = nullptr;
+    sa.discard_sorted_keys = true;  // k_emit reads the sorted compact ids only
     uint32_t depth_passes = 0;
     CK(launch_sort(sa, &depth_passes, stream));
     const int fin_a = depth_passes & 1;
@@ -281,6 +283,7 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     sp.num_sms = ctx->num_sms;
     sp.events = ctx->timers ? ctx->ev_sort : nullptr;
     sp.ranges = ctx->ranges;  // the last pass writes the tile ranges (tile_boundary.comp fused)
+    sp.discard_sorted_keys = !ctx->debug;  // only gsb_debug_download(GSB_BUF_KEYS) reads them; the blend uses vals + ranges
     CK(launch_ranges_init(ctx->ranges, T, stream));
     uint32_t passes = 0;
     CK(launch_sort(sp, &passes, stream));
@@ -311,6 +314,7 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     CK(cudaEventRecord(ctx->ev_done, stream));
     ctx->frame_pending = true;
     ctx->have_frame = true;
+    ctx->frame_debug = ctx->debug;
     ctx->last_w = W;
     ctx->last_h = H;
     ctx->last_tiles_x = tiles_x;
@@ -661,7 +665,7 @@ size_t gsb_debug_size(gsb_ctx* ctx, gsb_buffer which) {
     if (!ctx) return 0;
     const uint64_t n = ctx->n;
     if (which == GSB_BUF_COV3D) return (size_t)n * 6 * sizeof(float);
-    if (!ctx->have_frame || !ctx->debug) return 0;
+    if (!ctx->have_frame || !ctx->debug || !ctx->frame_debug) return 0;
     if (wait_frame(ctx) != GSB_OK) return 0;
     const uint64_t m = ctx->ctl_host->num_instances;
     switch (which) {

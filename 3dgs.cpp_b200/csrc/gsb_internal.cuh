@@ -100,6 +100,7 @@ struct SortParams {
     int num_sms;
     cudaEvent_t* events;       // optional: events[0] after the histogram, events[1 + p] after pass p
     uint2* ranges;             // optional (u32 keys): the last pass also produces the tile ranges (start, ~end)
+    bool discard_sorted_keys;  // the last pass writes payloads only (the caller never reads the sorted keys)
 };
 // Returns the number of passes P via *passes; sorted data ends in keys[P & 1].
 cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s);

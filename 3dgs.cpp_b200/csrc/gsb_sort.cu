@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
 #pragma unroll
             for (int it = 0; it < SORT_IPT; it++) {
                 if ((uint32_t)(it * SORT_THREADS + tid) < valid) {
-                    kout[g[it]] = k[it];
+                    if (kout != nullptr) kout[g[it]] = k[it];  // null: nobody reads the fully sorted keys (last pass)
                     vout[g[it]] = v[it];
                 }
             }
@@ -482,7 +482,8 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
     if (blocks == 0) blocks = 1;
     for (uint32_t pass = 0; pass < P; pass++) {
         const int src = pass & 1, dst = src ^ 1;
-        k_onesweep_pass<KeyT><<<blocks, SORT_THREADS, smem, s>>>(keys[src], p.vals[src], keys[dst], p.vals[dst], p.d_m, p.sc,
+        KeyT* kout = (pass + 1 == P && p.discard_sorted_keys) ? nullptr : keys[dst];
+        k_onesweep_pass<KeyT><<<blocks, SORT_THREADS, smem, s>>>(keys[src], p.vals[src], kout, p.vals[dst], p.d_m, p.sc,
                                                                  (int)pass, p.status, p.status_tiles, p.epoch_base + pass,
                                                                  pass + 1 == P ? p.ranges : nullptr);
         cudaError_t e = cudaGetLastError();
