@@ -336,10 +336,12 @@ def main():
         kd = "sort_depth(hist+4 onesweep passes over N_v)"
         alg = {
             "k_project": wl["n"] * 40 + nv * 192 + nv * (48 + 8 + 8),  # scene read + SH of survivors + record/AABB/depth key+payload
-            kd: nv * (4 + 16 * 4),                                     # histogram read + 4 x (8 B read + 8 B written)
+            kd: nv * (4 + 16 * 4 - 4),                                 # histogram read + 4 x (8 B read + 8 B written); the last pass writes no keys
             "k_emit": nv * (4 + 8) + 8 * M,                            # sorted ids + AABBs in, (tile id, payload) out
             "k_sort_hist": 4 * M,
-            "k_onesweep_pass": 16 * M + 4 * T_tiles,                   # 8 B read + 8 B written per (tile id, payload) pair (+ tile ranges, last pass)
+            # per launch, averaged over the passes: 8 B read + 8 B written per (tile id, payload) pair; the last pass
+            # writes payloads only (4 B) plus the tile ranges
+            "k_onesweep_pass": (16 * M * passes - 4 * M + 8 * T_tiles) / max(passes, 1),
             "k_blend": CONS * (4 + 36) + (nrows if world == 1 else H) * W * bpp,
         }
         dur = {"k_project": stage["preprocess_ms"], kd: stage["sort_depth_ms"], "k_emit": stage["preprocess_sort_ms"],

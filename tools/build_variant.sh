@@ -1,6 +1,6 @@
 #!/bin/bash
-# Build an A/B variant of libgsb200 with extra -D flags: tools/build_variant.sh <name> "<flags>"  ->  3dgs.cpp_b200/libgsb200_<name>.so
-# (run it with GSB200_LIB=... or tools/run_ab.sh libgsb200_<name>.so; variants are git-ignored)
+# Build an A/B variant of libgsb200 with extra -D flags: tools/build_variant.sh <name> "<flags>"  ->  3dgs.cpp_b200/libgsb200v_<name>.so
+# (run it with GSB200_LIB=... or tools/run_ab.sh libgsb200v_<name>.so; variants are git-ignored)
 set -e
 name=$1; flags=$2
 cd "$(dirname "$0")/../3dgs.cpp_b200"
@@ -12,5 +12,5 @@ for f in csrc/*.cu; do
   objs="$objs $o"
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libgsb200_$name.so $objs -cudart static
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libgsb200v_$name.so $objs -cudart static
 grep -h -A2 "k_blend\|k_onesweep\|k_project\|k_emit_cull\|k_sort_hist" /tmp/gsb_var_$name/*.log | grep -E "Used" | sort | uniq -c | head -20
