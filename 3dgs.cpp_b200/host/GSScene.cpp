@@ -1,9 +1,12 @@
 // GSScene.cpp -- see GSScene.h.  Mirrors the behaviour of src/GSScene.cpp:26-68,99-149 of the
-// reference: the header is scanned only for "element vertex <N>" (the property list is recorded
-// but does not drive the layout), then N fixed 62-float little-endian records follow.
+// reference for Inria-format files: "element vertex <N>", then N fixed 62-float little-endian
+// records.  Unlike the reference the header's property list is honoured (GSScene.h, PlyLayout):
+// the canonical list takes the verbatim path, anything else is gathered by property name.
 #include "GSScene.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <filesystem>
 #include <fstream>
 #include <sstream>
@@ -39,6 +42,12 @@ void GSScene::loadPlyHeader(std::ifstream& plyFile) {
         } else if (token == "property") {
             PlyProperty property;
             iss >> property.type >> property.name;
+            if (property.type == "list") {  // "property list <count type> <item type> <name>"
+                if (inVertexElement) throw std::runtime_error("list property in the vertex element of " + filename);
+                std::string itemType;
+                iss >> itemType >> property.name;
+                property.type = "list";
+            }
             (inVertexElement ? header.vertexProperties : header.faceProperties).push_back(property);
         } else if (token == "end_header") {
             headerEnd = true;
@@ -47,6 +56,91 @@ void GSScene::loadPlyHeader(std::ifstream& plyFile) {
     }
     if (!headerEnd) throw std::runtime_error("Could not find end of header");
     if (header.numVertices < 0) throw std::runtime_error("Negative vertex count in " + filename);
+    resolveLayout();
+}
+
+namespace {
+// canonical property names in record order
+std::vector<std::string> canonicalNames() {
+    std::vector<std::string> names = {"x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"};
+    for (int k = 0; k < 45; k++) names.push_back("f_rest_" + std::to_string(k));
+    names.push_back("opacity");
+    for (int k = 0; k < 3; k++) names.push_back("scale_" + std::to_string(k));
+    for (int k = 0; k < 4; k++) names.push_back("rot_" + std::to_string(k));
+    return names;
+}
+int plyTypeSize(const std::string& t) {
+    if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+    if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+    if (t == "int" || t == "uint" || t == "int32" || t == "uint32" || t == "float" || t == "float32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    return 0;
+}
+bool plyTypeIsFloat(const std::string& t) { return t == "float" || t == "float32"; }
+bool plyTypeIsDouble(const std::string& t) { return t == "double" || t == "float64"; }
+}  // namespace
+
+void GSScene::resolveLayout() {
+    layout = PlyLayout{};
+    for (int k = 0; k < 62; k++) {
+        layout.offset[k] = 4 * k;
+        layout.is_double[k] = 0;
+    }
+    const auto& props = header.vertexProperties;
+    if (!header.format.empty() && header.format != "binary_little_endian")
+        throw std::runtime_error("unsupported PLY format '" + header.format + "' in " + filename + " (binary_little_endian only)");
+    const std::vector<std::string> names = canonicalNames();
+    if (props.empty()) return;  // no list at all: the reference's assumption is all there is
+    bool same = props.size() == names.size();
+    for (size_t k = 0; same && k < names.size(); k++) same = props[k].name == names[k] && plyTypeIsFloat(props[k].type);
+    if (same) return;
+
+    // gather by name
+    layout.canonical = false;
+    for (int k = 0; k < 62; k++) layout.offset[k] = -1;
+    uint64_t at = 0;
+    int restCount = 0;
+    std::vector<int32_t> restOffset(45, -1);
+    std::vector<uint8_t> restDouble(45, 0);
+    for (const PlyProperty& pr : props) {
+        const int size = plyTypeSize(pr.type);
+        if (size == 0) throw std::runtime_error("unknown PLY property type '" + pr.type + "' in " + filename);
+        if (at > 0x7fffffffull) throw std::runtime_error("vertex record too large in " + filename);
+        const bool fl = plyTypeIsFloat(pr.type), db = plyTypeIsDouble(pr.type);
+        if (pr.name.rfind("f_rest_", 0) == 0) {
+            const int idx = std::atoi(pr.name.c_str() + 7);
+            if (idx < 0 || idx >= 45 || !(fl || db)) throw std::runtime_error("bad SH property '" + pr.name + "' in " + filename);
+            restOffset[idx] = static_cast<int32_t>(at);
+            restDouble[idx] = db;
+            restCount = std::max(restCount, idx + 1);
+        } else {
+            for (int k = 0; k < 62; k++) {
+                if (k >= 9 && k < 54) continue;  // f_rest slots are resolved below
+                if (names[k] == pr.name) {
+                    if (!(fl || db)) throw std::runtime_error("PLY property '" + pr.name + "' is not a float in " + filename);
+                    layout.offset[k] = static_cast<int32_t>(at);
+                    layout.is_double[k] = db;
+                }
+            }
+        }
+        at += static_cast<uint64_t>(size);
+    }
+    layout.stride = at;
+    // f_rest is channel-major with K = restCount / 3 coefficients per channel (K = 0, 3, 8, 15 for degree 0..3);
+    // coefficient j of channel c goes to the canonical slot 15 c + j, the missing higher bands stay zero
+    if (restCount % 3 != 0) throw std::runtime_error("f_rest count is not a multiple of 3 in " + filename);
+    const int K = restCount / 3;
+    if (K != 0 && K != 3 && K != 8 && K != 15) throw std::runtime_error("f_rest count matches no SH degree in " + filename);
+    layout.shDegree = K == 0 ? 0 : (K == 3 ? 1 : (K == 8 ? 2 : 3));
+    for (int c = 0; c < 3; c++)
+        for (int j = 0; j < K; j++) {
+            const int src = c * K + j;
+            if (restOffset[src] < 0) throw std::runtime_error("missing f_rest_" + std::to_string(src) + " in " + filename);
+            layout.offset[9 + 15 * c + j] = restOffset[src];
+            layout.is_double[9 + 15 * c + j] = restDouble[src];
+        }
+    for (int k : {0, 1, 2, 6, 7, 8, 54, 55, 56, 57, 58, 59, 60, 61})
+        if (layout.offset[k] < 0) throw std::runtime_error("missing PLY property '" + names[k] + "' in " + filename);
 }
 
 void GSScene::activateRecords(const float* records, uint64_t n, Vertex* out, unsigned threads) {
@@ -102,11 +196,33 @@ void GSScene::loadToHost() {
     // stream the records in bounded chunks: C5-scale files are 12 GB
     const uint64_t chunk = 1u << 20;
     std::vector<float> records(std::min(n, chunk) * kRecordFloats);
+    std::vector<unsigned char> raw;
+    if (!layout.canonical) raw.resize(std::min(n, chunk) * layout.stride);
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint64_t cnt = std::min(chunk, n - off);
-        plyFile.read(reinterpret_cast<char*>(records.data()), static_cast<std::streamsize>(cnt * kRecordFloats * sizeof(float)));
-        if (static_cast<uint64_t>(plyFile.gcount()) != cnt * kRecordFloats * sizeof(float))
-            throw std::runtime_error("Unexpected end of file in " + filename);
+        char* dst = layout.canonical ? reinterpret_cast<char*>(records.data()) : reinterpret_cast<char*>(raw.data());
+        const uint64_t bytes = cnt * layout.stride;
+        plyFile.read(dst, static_cast<std::streamsize>(bytes));
+        if (static_cast<uint64_t>(plyFile.gcount()) != bytes) throw std::runtime_error("Unexpected end of file in " + filename);
+        if (!layout.canonical) {  // gather the named fields into canonical 62-float records
+            for (uint64_t i = 0; i < cnt; i++) {
+                const unsigned char* src = raw.data() + i * layout.stride;
+                float* rec = records.data() + i * kRecordFloats;
+                for (int k = 0; k < 62; k++) {
+                    float v = 0.0f;
+                    if (layout.offset[k] >= 0) {
+                        if (layout.is_double[k]) {
+                            double d;
+                            std::memcpy(&d, src + layout.offset[k], sizeof d);
+                            v = static_cast<float>(d);
+                        } else {
+                            std::memcpy(&v, src + layout.offset[k], sizeof v);
+                        }
+                    }
+                    rec[k] = v;
+                }
+            }
+        }
         activateRecords(records.data(), cnt, hostVertices.data() + off);
     }
 }

@@ -14,6 +14,16 @@ struct PlyProperty {
     std::string name;
 };
 
+// Where the 62 canonical floats of one record (x y z | nx ny nz | f_dc 0-2 | f_rest 0-44 | opacity | scale 0-2 |
+// rot 0-3, src/GSScene.cpp:17-24) sit inside one on-disk vertex record of the file at hand.
+struct PlyLayout {
+    bool canonical = true;      // the file IS 62 packed floats in the canonical order: read records verbatim
+    uint64_t stride = 62 * 4;   // bytes per on-disk vertex record
+    int32_t offset[62];         // byte offset of canonical float k inside a record, -1 = absent (reads as 0)
+    uint8_t is_double[62];      // the source property is a 64-bit float
+    int shDegree = 3;           // highest SH degree present in the file (f_rest count 0 / 9 / 24 / 45)
+};
+
 struct PlyHeader {
     std::string format;
     int64_t numVertices = 0;
@@ -42,6 +52,11 @@ public:
 
     uint64_t getNumVertices() const { return static_cast<uint64_t>(header.numVertices); }
     const PlyHeader& getHeader() const { return header; }
+    // Layout derived from the header's property list.  The reference ignores the list and assumes
+    // the canonical record (src/GSScene.cpp:119-123,36-59); files with that list -- or with none -- take the same
+    // verbatim path here.  Other lists (extra properties, another order, SH degree < 3, double fields) are gathered
+    // by name; a missing required field, a list property or a non-little-endian-binary format is an error.
+    const PlyLayout& getLayout() const { return layout; }
     const std::vector<Vertex>& vertices() const { return hostVertices; }
     void releaseHostCopy() { std::vector<Vertex>().swap(hostVertices); }
 
@@ -52,6 +67,8 @@ public:
 private:
     std::string filename;
     PlyHeader header;
+    PlyLayout layout;
     std::vector<Vertex> hostVertices;
+    void resolveLayout();
     void loadPlyHeader(std::ifstream& plyFile);
 };

@@ -107,6 +107,77 @@ def test_truncated_ply_is_an_error(gs, tmp_path):
         gs.load_ply(path)
 
 
+CANON = (["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"] + [f"f_rest_{k}" for k in range(45)]
+         + ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"])
+
+
+def _write_custom_ply(path, fields, n, fmt="binary_little_endian"):
+    """fields: list of (name, ply type, numpy dtype, column array)."""
+    dt = np.dtype([(name, npt) for name, _, npt, _ in fields])
+    arr = np.zeros(n, dtype=dt)
+    for name, _, _, col in fields:
+        arr[name] = col
+    head = f"ply\nformat {fmt} 1.0\ncomment custom layout\nelement vertex {n}\n"
+    head += "".join(f"property {plyt} {name}\n" for name, plyt, _, _ in fields) + "end_header\n"
+    path.write_bytes(head.encode() + arr.tobytes())
+
+
+def test_ply_header_property_list_is_honoured(gs, tmp_path):
+    """shuffled order, extra properties, a double field, SH degree 1 (9 f_rest, channel-major)."""
+    n = 321
+    rec = gs.synth_records(5, n)
+    K = 3  # degree 1: 3 coefficients per channel
+    rest = rec[:, 9:54].reshape(n, 3, 15)
+    want = rec.copy()
+    want[:, 3:6] = 0.0  # normals are not stored in this file
+    w_rest = np.zeros((n, 3, 15), np.float32)
+    w_rest[:, :, :K] = rest[:, :, :K]
+    want[:, 9:54] = w_rest.reshape(n, 45)
+    col = {name: rec[:, k] for k, name in enumerate(CANON)}
+    fields = [("rot_3", "float", "<f4", col["rot_3"]), ("label", "uchar", "u1", np.arange(n) % 250),
+              ("opacity", "double", "<f8", col["opacity"].astype(np.float64))]
+    fields += [(f"f_rest_{c * K + j}", "float", "<f4", rest[:, c, j]) for c in range(3) for j in range(K)]
+    fields += [(nm, "float32", "<f4", col[nm]) for nm in ("z", "y", "x", "scale_2", "scale_0", "scale_1", "rot_0", "rot_1", "rot_2")]
+    fields += [("id", "int", "<i4", np.arange(n)), ("f_dc_1", "float", "<f4", col["f_dc_1"]), ("f_dc_0", "float", "<f4", col["f_dc_0"]),
+               ("f_dc_2", "float", "<f4", col["f_dc_2"])]
+    path = tmp_path / "custom.ply"
+    _write_custom_ply(path, fields, n)
+    got = gs.load_ply(path)
+    assert np.array_equal(got, gs.activate_records(want))
+
+
+def test_ply_without_property_list_is_read_like_the_reference(gs, tmp_path):
+    rec = gs.synth_records(6, 17)
+    path = tmp_path / "bare.ply"
+    path.write_bytes(b"ply\nformat binary_little_endian 1.0\nelement vertex 17\nend_header\n" + rec.tobytes())
+    assert np.array_equal(gs.load_ply(path), gs.activate_records(rec))
+
+
+@pytest.mark.parametrize("case", ["missing_opacity", "ascii", "bad_rest_count", "int_position", "list_property"])
+def test_malformed_ply_headers_are_errors(gs, tmp_path, case):
+    n = 4
+    rec = gs.synth_records(7, n)
+    col = {name: rec[:, k] for k, name in enumerate(CANON)}
+    names = [nm for nm in CANON if not nm.startswith("n")]
+    fields = [(nm, "float", "<f4", col[nm]) for nm in names]
+    fmt = "binary_little_endian"
+    path = tmp_path / f"{case}.ply"
+    if case == "missing_opacity":
+        fields = [f for f in fields if f[0] != "opacity"]
+    elif case == "ascii":
+        fmt = "ascii"
+    elif case == "bad_rest_count":
+        fields = [f for f in fields if f[0] != "f_rest_44"]
+    elif case == "int_position":
+        fields = [("x", "int", "<i4", np.zeros(n))] + [f for f in fields if f[0] != "x"]
+    _write_custom_ply(path, fields, n, fmt)
+    if case == "list_property":
+        data = path.read_bytes().replace(b"end_header\n", b"property list uchar int vertex_indices\nend_header\n", 1)
+        path.write_bytes(data)
+    with pytest.raises(RuntimeError):
+        gs.load_ply(path)
+
+
 def test_synth_is_counter_based(gs):
     whole = gs.synth_records(42, 3000)
     parts = np.concatenate([gs.synth_records(42, 1000, first=0), gs.synth_records(42, 2000, first=1000)])
