@@ -1,6 +1,8 @@
 // gs_viewer_headless -- the reference viewer's command line (apps/viewer/main.cpp:12-98) without a window:
 //   gs_viewer_headless [-d DEVICE] [-w WIDTH] [-h HEIGHT] [-v] [--frames N] [--camera x,y,z[,qw,qx,qy,qz]]
-//                      [--fov DEG] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply
+//                      [--fov DEG] [--camera-path poses.txt] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply
+// --camera-path: one pose per line `x y z qw qx qy qz [fov]` (# comments); `--frames` frames are rendered at each pose
+// and one JSON line is printed per pose (record M for every timed camera).
 // Loads the .ply through GSScene, renders N frames through Renderer::draw() (B8G8R8A8 like the swapchain),
 // prints the six per-stage timers + `instances` (Renderer.cpp:85-100,540) as one JSON line per run and
 // optionally writes the last frame as a binary PPM.  Environment: VKGS_PHYSICAL_DEVICE like the viewer.
@@ -17,12 +19,12 @@
 
 static void usage() {
     std::puts("usage: gs_viewer_headless [-d device] [-w width] [-h height] [-v] [--frames n] [--camera x,y,z[,qw,qx,qy,qz]]\n"
-              "                          [--fov deg] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply");
+              "                          [--fov deg] [--camera-path poses.txt] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply");
 }
 
 int main(int argc, char** argv) {
     Renderer::Configuration cfg;
-    std::string out_path, scene;
+    std::string out_path, scene, path_file;
     uint32_t frames = 1;
     bool verbose = false, cull = false;
     float cam[7] = {0, 0, 0, 1, 0, 0, 0};
@@ -46,6 +48,7 @@ int main(int argc, char** argv) {
         else if (a == "--mode") cfg.mode = std::string(next()) == "fast" ? GSB_MODE_FAST : GSB_MODE_EXACT;
         else if (a == "--cull") cull = true;
         else if (a == "--out") out_path = next();
+        else if (a == "--camera-path") path_file = next();
         else if (a == "--camera") {
             int k = 0;
             for (char* tok = std::strtok(const_cast<char*>(next()), ","); tok && k < 7; tok = std::strtok(nullptr, ",")) cam[k++] = static_cast<float>(std::atof(tok));
@@ -65,20 +68,43 @@ int main(int argc, char** argv) {
         renderer.initialize();
         const double load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (cull && gsb_set_tile_cull(renderer.context(), 1) != GSB_OK) throw std::runtime_error("gsb_set_tile_cull failed");
-        renderer.camera.position = {cam[0], cam[1], cam[2]};
-        renderer.camera.rotation = {cam[3], cam[4], cam[5], cam[6]};
-        renderer.camera.fov = fov;
+        struct Pose {
+            float v[7];
+            float fov;
+        };
+        std::vector<Pose> poses;
+        if (path_file.empty()) {
+            poses.push_back(Pose{{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5], cam[6]}, fov});
+        } else {
+            std::ifstream pf(path_file);
+            if (!pf) throw std::runtime_error("cannot open camera path: " + path_file);
+            std::string line;
+            while (std::getline(pf, line)) {
+                if (line.empty() || line[0] == '#') continue;
+                Pose p{{0, 0, 0, 1, 0, 0, 0}, fov};
+                const int got = std::sscanf(line.c_str(), "%f %f %f %f %f %f %f %f", &p.v[0], &p.v[1], &p.v[2], &p.v[3], &p.v[4], &p.v[5], &p.v[6], &p.fov);
+                if (got < 7) throw std::runtime_error("bad camera path line: " + line);
+                poses.push_back(p);
+            }
+            if (poses.empty()) throw std::runtime_error("camera path is empty: " + path_file);
+        }
         if (verbose) std::fprintf(stderr, "loaded %llu Gaussians in %.1f ms\n", (unsigned long long)renderer.getScene()->getNumVertices(), load_ms);
-        const auto t1 = std::chrono::steady_clock::now();
-        renderer.run(frames);
-        const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
-        const gsb_stats s = renderer.retrieveTimestamps();
-        std::printf("{\"scene\": \"%s\", \"gaussians\": %llu, \"width\": %u, \"height\": %u, \"frames\": %u, \"fps_wall\": %.2f, "
-                    "\"instances\": %llu, \"instances_aabb\": %llu, \"visible\": %llu, \"preprocess_ms\": %.4f, \"prefix_sum_ms\": %.4f, "
-                    "\"preprocess_sort_ms\": %.4f, \"sort_ms\": %.4f, \"tile_boundary_ms\": %.4f, \"render_ms\": %.4f, \"frame_ms\": %.4f}\n",
-                    scene.c_str(), (unsigned long long)s.num_gaussians, cfg.width, cfg.height, frames, 1000.0 * frames / wall_ms,
-                    (unsigned long long)s.num_instances, (unsigned long long)s.num_instances_aabb, (unsigned long long)s.num_visible,
-                    s.preprocess_ms, s.prefix_sum_ms, s.preprocess_sort_ms, s.sort_ms, s.tile_boundary_ms, s.render_ms, s.frame_ms);
+        for (size_t pi = 0; pi < poses.size(); pi++) {
+            const Pose& po = poses[pi];
+            renderer.camera.position = {po.v[0], po.v[1], po.v[2]};
+            renderer.camera.rotation = {po.v[3], po.v[4], po.v[5], po.v[6]};
+            renderer.camera.fov = po.fov;
+            const auto t1 = std::chrono::steady_clock::now();
+            renderer.run(frames);
+            const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+            const gsb_stats s = renderer.retrieveTimestamps();
+            std::printf("{\"scene\": \"%s\", \"pose\": %zu, \"gaussians\": %llu, \"width\": %u, \"height\": %u, \"frames\": %u, \"fps_wall\": %.2f, "
+                        "\"instances\": %llu, \"instances_aabb\": %llu, \"visible\": %llu, \"preprocess_ms\": %.4f, \"prefix_sum_ms\": %.4f, "
+                        "\"preprocess_sort_ms\": %.4f, \"sort_ms\": %.4f, \"tile_boundary_ms\": %.4f, \"render_ms\": %.4f, \"frame_ms\": %.4f}\n",
+                        scene.c_str(), pi, (unsigned long long)s.num_gaussians, cfg.width, cfg.height, frames, 1000.0 * frames / wall_ms,
+                        (unsigned long long)s.num_instances, (unsigned long long)s.num_instances_aabb, (unsigned long long)s.num_visible,
+                        s.preprocess_ms, s.prefix_sum_ms, s.preprocess_sort_ms, s.sort_ms, s.tile_boundary_ms, s.render_ms, s.frame_ms);
+        }
         if (!out_path.empty()) {
             const auto& px = renderer.frame();  // B8G8R8A8
             std::ofstream f(out_path, std::ios::binary);

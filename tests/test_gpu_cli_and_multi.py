@@ -40,6 +40,15 @@ def test_headless_viewer_cli(gs, oracle, tmp_path):
     assert data.startswith(head)
     rgb = np.frombuffer(data[len(head):], np.uint8).reshape(480, 640, 3)
     assert np.array_equal(rgb, oracle.pack_unorm8(ref["rgba"])[..., :3])
+    # camera path: one JSON line per pose, pose 0 = the camera above, pose 1 looks from further away
+    poses = tmp_path / "poses.txt"
+    poses.write_text("# x y z qw qx qy qz [fov]\n0 0 5 1 0 0 0\n0 0 7 1 0 0 0 60\n")
+    r = subprocess.run([str(exe), "-w", "640", "-h", "480", "--camera-path", str(poses), str(ply)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = [json.loads(l) for l in r.stdout.strip().splitlines()]
+    assert [l["pose"] for l in lines] == [0, 1] and lines[0]["instances"] == ref["m"]
+    u2 = gs.uniforms_from_camera([0, 0, 7], [1, 0, 0, 0], 60.0, 0.1, 1000.0, 640, 480)
+    assert lines[1]["instances"] == oracle.render_frame(vtx, oracle.cov3d(vtx), u2)["m"]
     # missing file: logged, non-zero exit (the reference catches at top level, main.cpp:94-105)
     r = subprocess.run([str(exe), "/nonexistent.ply"], capture_output=True, text=True)
     assert r.returncode != 0 and "File does not exist" in r.stderr
