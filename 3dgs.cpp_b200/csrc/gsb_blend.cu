@@ -85,6 +85,9 @@ struct __align__(16) StagedRec {
     float4 r2;  // g b - -
 };
 
+#ifndef GSB_BLEND_PREDICATED
+#define GSB_BLEND_PREDICATED 1
+#endif
 #ifndef GSB_BLEND_MIN_BLOCKS
 #define GSB_BLEND_MIN_BLOCKS 5  // <= 51 registers, 5 CTAs per SM (measured: 0.873 ms; 4 CTAs 0.886, 6 CTAs 0.891, 80 registers 0.972)
 #endif
@@ -166,6 +169,21 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
                         fin_k = k;
                         ok = false;
                     }
+#if GSB_BLEND_PREDICATED
+                    // select form: the products are computed unconditionally, only the four state updates are predicated
+                    if (MODE == GSB_MODE_EXACT) {
+                        const float n0 = c0 + (b.w * alpha) * T, n1 = c1 + (gb.x * alpha) * T, n2 = c2 + (gb.y * alpha) * T;  // :87
+                        c0 = ok ? n0 : c0;
+                        c1 = ok ? n1 : c1;
+                        c2 = ok ? n2 : c2;
+                    } else {
+                        const float w = alpha * T;
+                        c0 = ok ? fmaf(b.w, w, c0) : c0;
+                        c1 = ok ? fmaf(gb.x, w, c1) : c1;
+                        c2 = ok ? fmaf(gb.y, w, c2) : c2;
+                    }
+                    T = ok ? test_T : T;  // :88
+#else
                     if (ok) {
                         if (MODE == GSB_MODE_EXACT) {
                             c0 = c0 + (b.w * alpha) * T;  // :87
@@ -179,6 +197,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
                         }
                         T = test_T;  // :88
                     }
+#endif
                 }
             }
             if (fin_k != 0xffffffffu) used = base - range.x + (s_list[warp][fin_k] - rec_sh) / (uint32_t)sizeof(StagedRec) + 1;
