@@ -24,23 +24,21 @@ namespace {
 constexpr int BLEND_THREADS = 256;
 constexpr unsigned FULL = 0xffffffffu;
 
-// Bit-defined exp for x in [-87, 0]; mirrors gso_exp_shared() in oracle/gs_oracle.c op for op.
+// Bit-defined exp for x in [-87, 0]; mirrors gso_exp_shared() in oracle/gs_oracle.c op for op: Cody-Waite
+// reduction, degree-5 Horner with the constant term 1, 2^n applied through the exponent bits (13 instructions).
 __device__ __forceinline__ float exp_shared(float x) {
     x = fmaxf(x, -87.0f);
     const float t = __fmul_rn(x, 1.44269504088896341f);
-    const float n = __fsub_rn(__fadd_rn(t, 12582912.0f), 12582912.0f);  // rint(t)
+    const float tm = __fadd_rn(t, 12582912.0f);  // low mantissa bits = rint(t) in two's complement
+    const float n = __fsub_rn(tm, 12582912.0f);
     float r = __fmaf_rn(n, -0.693359375f, x);
     r = __fmaf_rn(n, 2.12194440e-4f, r);
-    const float z = __fmul_rn(r, r);
-    float y = __fmaf_rn(1.9875691500e-4f, r, 1.3981999507e-3f);
-    y = __fmaf_rn(y, r, 8.3334519073e-3f);
-    y = __fmaf_rn(y, r, 4.1665795894e-2f);
-    y = __fmaf_rn(y, r, 1.6666665459e-1f);
-    y = __fmaf_rn(y, r, 5.0000001201e-1f);
-    y = __fmaf_rn(y, z, r);
-    y = __fadd_rn(y, 1.0f);
-    const int ni = (int)n;
-    return __fmul_rn(y, __int_as_float((ni + 127) << 23));
+    float p = __fmaf_rn(8.290082216262817e-3f, r, 4.1899293661117554e-2f);
+    p = __fmaf_rn(p, r, 1.6667647659778595e-1f);
+    p = __fmaf_rn(p, r, 4.9999138712882996e-1f);
+    p = __fmaf_rn(p, r, 9.999997019767761e-1f);
+    p = __fmaf_rn(p, r, 1.0f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(tm) << 23));
 }
 
 // shared-memory loads by 32-bit shared-window address (one LDS each, immediate offsets, no generic-pointer arithmetic)
