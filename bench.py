@@ -302,6 +302,11 @@ def main():
     e2e_sync_s = time.perf_counter() - t0
 
     dev_fb = [torch.zeros((max(nrows, 1), W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)]
+    # N > 1: the bands are all-gathered on the device (as in `value`) and rank 0 copies the WHOLE frame to its host
+    # memory every step, so the end-to-end product is the same full framebuffer as at N = 1.
+    full_fb = [torch.zeros((world * rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    host_full = [torch.empty((world * rows_per * 16, W, bpp), dtype=torch.uint8).pin_memory() for _ in range(2)] if (world > 1 and rank == 0) else None
+    band_fb = [torch.zeros((rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     copy_stream = torch.cuda.Stream(device=dev)
     rendered = [torch.cuda.Event() for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
@@ -309,7 +314,19 @@ def main():
     t0 = time.perf_counter()
     for i in range(args.steps):
         k = i & 1
-        if nrows:
+        if world > 1:
+            if i >= 2:
+                stream.wait_event(copied[k])  # frame i-2 has left full_fb[k]
+            if rb < re:
+                ctx.render_into(cams[i % NUM_CAMERAS], band_fb[k].data_ptr(), fmt, rows=band, stream=stream, sync=False)
+            dist.all_gather_into_tensor(full_fb[k].view(-1), band_fb[k].view(-1))
+            rendered[k].record(stream)
+            if rank == 0:
+                copy_stream.wait_event(rendered[k])
+                with torch.cuda.stream(copy_stream):
+                    host_full[k].copy_(full_fb[k], non_blocking=True)
+            copied[k].record(copy_stream)
+        elif nrows:
             if i >= 2:
                 stream.wait_event(copied[k])  # frame i-2 has left dev_fb[k]
             ctx.render_into(cams[i % NUM_CAMERAS], dev_fb[k].data_ptr(), fmt, rows=(rb, re), stream=stream, sync=False)
@@ -372,8 +389,9 @@ def main():
                        "cameras": NUM_CAMERAS, "l2": "inputs (1.3 GB scene + 0.4 GB keys) larger than the 126 MB L2; no flush",
                        "parallelism": f"tile-row bands x{world}" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 160,
-                    "d2h_bytes_per_step": int(nrows * W * bpp) + 64,
-                    "api": "gsb_render_async(host UBO) + cudaMemcpyAsync of every BGRA8 frame to pinned host memory, double buffered",
+                    "d2h_bytes_per_step": (int(world * rows_per * 16 * W * bpp) if world > 1 else int(nrows * W * bpp)) + 64,
+                    "api": ("gsb_render_async(host UBO) per band + NCCL all-gather on the device + cudaMemcpyAsync of every whole BGRA8 frame to rank 0's pinned host memory, double buffered"
+                            if world > 1 else "gsb_render_async(host UBO) + cudaMemcpyAsync of every BGRA8 frame to pinned host memory, double buffered"),
                     "sync_value": e2e_sync_fps, "sync_api": "gsb_render(host UBO -> host BGRA8), one blocking call per frame"},
             "gpu_launches": int((9 + passes) * args.steps),  # project, hist+4 passes (depth), emit, hist+P passes (tile; the last one also writes the tile ranges), blend
             "clocks": clocks,
