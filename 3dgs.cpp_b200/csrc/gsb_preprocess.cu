@@ -297,7 +297,13 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
 // ------------------------------------------------------------------------------------------
 // k_emit
 // ------------------------------------------------------------------------------------------
-constexpr int EMIT_WIN = 4096;   // instances staged in shared memory per window
+#ifndef GSB_EMIT_WIN
+#define GSB_EMIT_WIN 4096
+#endif
+#ifndef GSB_EMIT_MIN_BLOCKS
+#define GSB_EMIT_MIN_BLOCKS 5  // <= 51 registers (an unannotated kernel got 48; minBlocks = 1 makes ptxas take 69)
+#endif
+constexpr int EMIT_WIN = GSB_EMIT_WIN;   // instances staged in shared memory per window
 constexpr uint32_t EMIT_BIG = 128;  // Gaussians covering more tiles than this are expanded by the whole block
 
 __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ EmitParams P) {
@@ -547,7 +553,7 @@ __device__ __forceinline__ void cull_row_span(const CullGauss& g, uint32_t ty, i
     }
 }
 
-__global__ void __launch_bounds__(PRE_THREADS) k_emit_cull(const __grid_constant__ EmitParams P) {
+__global__ void __launch_bounds__(PRE_THREADS, GSB_EMIT_MIN_BLOCKS) k_emit_cull(const __grid_constant__ EmitParams P) {
     __shared__ uint32_t s_chunk;
     __shared__ uint32_t s_wnt[PRE_THREADS / 32];
     __shared__ unsigned long long s_base;

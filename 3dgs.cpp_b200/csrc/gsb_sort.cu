@@ -21,7 +21,7 @@ namespace {
 #endif
 constexpr int SORT_IPT = 16;  // pairs per thread
 #ifndef GSB_SORT_THREADS
-#define GSB_SORT_THREADS 512  // 512 threads x 16 = 8192-pair tiles, ONE persistent CTA per SM: fewer tiles in flight keeps the look-back chain short (measured 0.240 vs 0.257 ms per pass against 2 x 256)
+#define GSB_SORT_THREADS 256  // 256 threads x 16 = 4096-pair tiles, TWO persistent CTAs per SM.  With ballot ranking one 512-thread CTA per SM was faster (shorter look-back chain: 0.240 vs 0.257 ms per pass); with atomicOr matching the two layouts tie on the 17 M-pair tile sort (0.132 ms) and 2 x 256 wins on the 2.6 M-pair depth sort (0.132 vs 0.142 ms for hist + 4 passes: finer tiles balance 148 SMs better)
 #endif
 constexpr int SORT_THREADS = GSB_SORT_THREADS;
 constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;
@@ -29,6 +29,9 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int RADIX = 256;
 constexpr unsigned FULL = 0xffffffffu;
 
+#ifndef GSB_HIST_CTAS
+#define GSB_HIST_CTAS 3  // k_sort_hist CTAs per SM (measured on 17 M keys: 2 -> 0.049 ms, 3 or 4 -> 0.044)
+#endif
 constexpr int HIST_THREADS = 512;
 constexpr int HIST_IPT = 8;
 constexpr int HIST_TILE = HIST_THREADS * HIST_IPT;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(HIST_THREADS) k_sort_hist(const KeyT* __restri
 // ------------------------------------------------------------------------------------------
 // One Onesweep pass (replaces one hist.comp + sort.comp pair).
 //
-// Persistent kernel, one 512-thread CTA per SM, tile = 8192 pairs.
+// Persistent kernel, two 256-thread CTAs per SM, tile = 4096 pairs (GSB_SORT_THREADS).
 //  * TMA: the next tile's keys and payloads are fetched by cp.async.bulk (SASS UBLKCP) into the
 //    second shared-memory buffer while the current tile is ranked and scattered; completion is an
 //    mbarrier transaction count.  No registers are tied up by loads in flight.
@@ -464,7 +467,7 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
     KeyT* keys[2] = {static_cast<KeyT*>(p.keys[0]), static_cast<KeyT*>(p.keys[1])};
     {  // histogram: persistent grid-stride, at most 2 CTAs per SM
         uint32_t blocks = (hint + HIST_TILE - 1) / HIST_TILE;
-        const uint32_t cap = (uint32_t)p.num_sms * 2;
+        const uint32_t cap = (uint32_t)p.num_sms * GSB_HIST_CTAS;
         if (blocks > cap) blocks = cap;
         if (blocks == 0) blocks = 1;
         cudaError_t e = launch_hist<KeyT>(keys[0], p, P, blocks, s);
