@@ -9,7 +9,8 @@
 //     alpha < 1/255 cut (with an fp32 error margin) can never contribute, so that warp never
 //     touches the record (bit-identical result: those pairs hit `continue` in render.comp:78);
 //   * each warp compacts the batch with one ballot per 32 records and walks only its survivors,
-//     reading each record as a shared-memory broadcast.
+//     reading each record as a shared-memory broadcast; the walk is branch-free per lane (the
+//     shader's `continue`s and `break` are predicates on the four state updates).
 // The per-pixel `break` (render.comp:83-85) becomes a per-lane done flag + warp / block votes.
 //
 // EXACT mode: -fmad=false, ops in render.comp's order, exp = the fixed IEEE sequence below

@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(HIST_THREADS) k_sort_hist(const KeyT* __restri
 //  * TMA: the next tile's keys and payloads are fetched by cp.async.bulk (SASS UBLKCP) into the
 //    second shared-memory buffer while the current tile is ranked and scattered; completion is an
 //    mbarrier transaction count.  No registers are tied up by loads in flight.
-//  * ranking: warp-striped, 8 ballots per 8-bit digit (constant time; MATCH.ANY costs time
-//    proportional to the number of distinct digits in the warp), per-warp digit counters in smem.
+//  * ranking: warp-striped.  u32 keys: every lane ORs its lane bit into a per-warp, per-digit mask
+//    word in shared memory and reads the word back (= its peers); u64 keys (no room for the mask
+//    plane): 8 ballots per 8-bit digit.  MATCH.ANY is avoided: its cost grows with the number of
+//    distinct digits in the warp.  Per-warp digit counters in smem give the stable rank.
 //  * the tile is permuted IN PLACE in shared memory (raw -> digit-sorted), so the global scatter
 //    writes runs of consecutive addresses per digit (coalesced key / payload stores).
 //  * chained scan: tile aggregate published right after ranking, decoupled look-back per digit
