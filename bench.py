@@ -402,6 +402,13 @@ def main():
             "sort_keys_per_s": M / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
             "blend_pair_evals_per_s": CONS * 256 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
         }
+        try:  # M for every timed camera, median / p95 of the per-camera frame time (library timers)
+            fm = [float(x) for x in stage_acc.get("frame_ms", [])]
+            out["per_camera"] = {"frame_ms": fm, "instances": [int(x) for x in m_acc],
+                                 "frame_ms_median": float(np.median(fm)) if fm else None,
+                                 "frame_ms_p95": float(np.percentile(fm, 95)) if fm else None}
+        except Exception as exc:  # reporting only: never lose the bench line over it
+            out["per_camera"] = {"error": str(exc)}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_oracle_sample(wl, vtx, cams[0], 20.0)
             out["cpu_baseline"] = {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
