@@ -796,11 +796,12 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
     }
 }
 
-int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, uint64_t m,
-                   uint32_t key_bits, void* stream) {
+// shared body of gsb_sort_pairs (u64 keys) and gsb_sort_pairs32 (u32 keys)
+static int sort_pairs_impl(gsb_ctx* ctx, void* keys, uint32_t* vals, void* keys_tmp, uint32_t* vals_tmp, uint64_t m,
+                           uint32_t key_bits, int key_bytes, void* stream, const char* what) {
     if (!ctx) return GSB_ERR_INVALID;
     if (m == 0) return GSB_OK;
-    if (!keys || !vals || !keys_tmp || !vals_tmp || key_bits == 0 || key_bits > 64) return fail(ctx, GSB_ERR_INVALID, "bad argument");
+    if (!keys || !vals || !keys_tmp || !vals_tmp || key_bits == 0 || key_bits > 8u * (uint32_t)key_bytes) return fail(ctx, GSB_ERR_INVALID, "bad argument");
     if (m >= (1ull << 30)) return fail(ctx, GSB_ERR_INVALID, "sort limited to 2^30 - 1 pairs");
     CK(cudaSetDevice(ctx->device));
     int rc = wait_frame(ctx);
@@ -817,7 +818,7 @@ int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
     SortParams sp{};
     sp.keys[0] = keys;
     sp.keys[1] = keys_tmp;
-    sp.key_bytes = 8;
+    sp.key_bytes = key_bytes;
     sp.vals[0] = vals;
     sp.vals[1] = vals_tmp;
     sp.d_m = &ctx->ctl->num_instances;
@@ -833,13 +834,23 @@ int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_
     uint32_t passes = 0;
     if (e == cudaSuccess) e = launch_sort(sp, &passes, s);
     if (e == cudaSuccess && (passes & 1)) {  // odd pass count: bring the result back to the "Even" buffers
-        e = cudaMemcpyAsync(keys, keys_tmp, m * 8, cudaMemcpyDeviceToDevice, s);
+        e = cudaMemcpyAsync(keys, keys_tmp, m * (size_t)key_bytes, cudaMemcpyDeviceToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(vals, vals_tmp, m * 4, cudaMemcpyDeviceToDevice, s);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // m32/status lifetime
     cudaFree(status);
-    if (e != cudaSuccess) return fail(ctx, GSB_ERR_CUDA, "gsb_sort_pairs", e);
+    if (e != cudaSuccess) return fail(ctx, GSB_ERR_CUDA, what, e);
     return GSB_OK;
+}
+
+int gsb_sort_pairs(gsb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp, uint64_t m,
+                   uint32_t key_bits, void* stream) {
+    return sort_pairs_impl(ctx, keys, vals, keys_tmp, vals_tmp, m, key_bits, 8, stream, "gsb_sort_pairs");
+}
+
+int gsb_sort_pairs32(gsb_ctx* ctx, uint32_t* keys, uint32_t* vals, uint32_t* keys_tmp, uint32_t* vals_tmp, uint64_t m,
+                     uint32_t key_bits, void* stream) {
+    return sort_pairs_impl(ctx, keys, vals, keys_tmp, vals_tmp, m, key_bits, 4, stream, "gsb_sort_pairs32");
 }
 
 }  // extern "C"

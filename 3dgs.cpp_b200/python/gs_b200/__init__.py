@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [  # every symbol include/gs_b200.h declares
     "gsb_abi_version", "gsb_device_count", "gsb_create", "gsb_destroy", "gsb_last_error",
     "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers", "gsb_set_tile_cull",
     "gsb_reserve_instances", "gsb_render", "gsb_render_async", "gsb_get_stats", "gsb_debug_size",
-    "gsb_debug_download", "gsb_sort_pairs",
+    "gsb_debug_download", "gsb_sort_pairs", "gsb_sort_pairs32",
 ]
 HOST_EXPORTED_SYMBOLS = [  # host/gs_b200_host.h
     "gsh_last_error", "gsh_initialize", "gsh_draw", "gsh_pan_translation", "gsh_movement", "gsh_cleanup",
@@ -107,6 +107,7 @@ lib.gsb_debug_size.argtypes = [_vp, C.c_int]
 lib.gsb_debug_size.restype = C.c_size_t
 lib.gsb_debug_download.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
 lib.gsb_sort_pairs.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp]
+lib.gsb_sort_pairs32.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp]
 
 host.gsh_last_error.restype = C.c_char_p
 host.gsh_initialize.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
@@ -333,6 +334,10 @@ class Context:
     def sort_pairs(self, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, m, key_bits=64, stream=None):
         self._ck(lib.gsb_sort_pairs(self.h, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, m, key_bits,
                                     stream_ptr(stream)))
+
+    def sort_pairs32(self, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, m, key_bits=32, stream=None):
+        self._ck(lib.gsb_sort_pairs32(self.h, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, m, key_bits,
+                                      stream_ptr(stream)))
 
 
 # ---------------------------------------------------------------- the C++ host Renderer (vkgs_* style bridge)

@@ -180,6 +180,11 @@ int gsb_debug_download(gsb_ctx *ctx, gsb_buffer which, void *dst, size_t bytes);
  * keys/vals (the "Even" buffers, Renderer.cpp:641); keys_tmp/vals_tmp are the "Odd" buffers. */
 int gsb_sort_pairs(gsb_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
                    uint64_t m, uint32_t key_bits, void *stream);
+/* The same operator over u32 keys (key_bits <= 32): the instantiation the frame itself runs twice -- depth
+ * bits over the visible Gaussians, tile ids over the instances (the reference's passes 0-3 and 4-7 of the same
+ * loop, Renderer.cpp:598-629). */
+int gsb_sort_pairs32(gsb_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
+                     uint64_t m, uint32_t key_bits, void *stream);
 
 #ifdef __cplusplus
 }

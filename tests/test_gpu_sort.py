@@ -50,3 +50,42 @@ def test_sort_constant_and_presorted(gs, oracle, ctx):
         ks, vs = run_sort(gs, ctx, keys, vals, 48)
         rk, rv = oracle.sort_pairs(keys, vals)
         assert np.array_equal(ks, rk) and np.array_equal(vs, rv)
+
+
+def run_sort32(gs, ctx, keys, vals, key_bits):
+    dev = torch.device("cuda:0")
+    k = torch.from_numpy(keys.view(np.int32)).to(dev)
+    v = torch.from_numpy(vals.view(np.int32)).to(dev)
+    kt, vt = torch.empty_like(k), torch.empty_like(v)
+    torch.cuda.synchronize()
+    ctx.sort_pairs32(k.data_ptr(), v.data_ptr(), kt.data_ptr(), vt.data_ptr(), keys.size, key_bits)
+    torch.cuda.synchronize()
+    return k.cpu().numpy().view(np.uint32), v.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("m", [1, 33, 4095, 4096, 4097, 12_289, 250_001, 3_000_000])
+@pytest.mark.parametrize("key_bits", [32, 24, 15, 8, 3])
+def test_sort32_random(gs, ctx, m, key_bits):
+    """u32 keys: the instantiation the frame runs (depth bits / tile ids) with the atomicOr digit matching."""
+    rng = np.random.default_rng(m * 17 + key_bits)
+    keys = rng.integers(0, 2**32, size=m, dtype=np.uint64).astype(np.uint32)
+    if key_bits < 32:
+        keys &= np.uint32((1 << key_bits) - 1)
+    vals = np.arange(m, dtype=np.uint32)
+    ks, vs = run_sort32(gs, ctx, keys, vals, key_bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ks, keys[order])
+    assert np.array_equal(vs, vals[order])  # stable: equal keys keep input order
+
+
+def test_sort32_skewed_digits(gs, ctx):
+    """Whole warps sharing one digit, runs of equal keys (a Gaussian's instances), one hot tile id."""
+    m = 700_000
+    rng = np.random.default_rng(3)
+    runs = np.repeat(rng.integers(0, 17_600, size=m // 7, dtype=np.uint64).astype(np.uint32), 7)[:m]
+    hot = np.where(rng.random(m) < 0.6, np.uint32(4242), runs).astype(np.uint32)
+    for keys, bits in ((runs, 15), (hot, 15), (np.zeros(m, np.uint32), 15), (np.full(m, 0xFFFFFFFF, np.uint32), 32)):
+        vals = rng.permutation(m).astype(np.uint32)
+        ks, vs = run_sort32(gs, ctx, keys.copy(), vals, bits)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(ks, keys[order]) and np.array_equal(vs, vals[order])
