@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(HIST_THREADS) k_sort_hist(const KeyT* __restri
 //    second shared-memory buffer while the current tile is ranked and scattered; completion is an
 //    mbarrier transaction count.  No registers are tied up by loads in flight.
 //  * ranking: warp-striped.  u32 keys: every lane ORs its lane bit into a per-warp, per-digit mask
-//    word in shared memory and reads the word back (= its peers); u64 keys (no room for the mask
-//    plane): 8 ballots per 8-bit digit.  MATCH.ANY is avoided: its cost grows with the number of
+//    word in shared memory and reads the word back (= its peers); u64 keys (gsb_sort_pairs, off the
+//    frame path): 8 ballots per 8-bit digit.  MATCH.ANY is avoided: its cost grows with the number of
 //    distinct digits in the warp.  Per-warp digit counters in smem give the stable rank.
 //  * the tile is permuted IN PLACE in shared memory (raw -> digit-sorted), so the global scatter
 //    writes runs of consecutive addresses per digit (coalesced key / payload stores).
@@ -134,7 +134,7 @@ struct PassSmem {
     KeyT keys[2][SORT_TILE];            // double buffer: current / prefetch
     uint32_t vals[2][SORT_TILE];
     uint32_t whist[SORT_WARPS][RADIX];  // per-warp digit counters -> exclusive offsets across warps
-    // per-warp lane masks per digit (atomicOr matching), always left zero; the u64 tile has no room for it
+    // per-warp lane masks per digit (atomicOr matching), always left zero; u32 keys only (the frame's instantiation)
     uint32_t match[kMatchAtomic<KeyT> ? SORT_WARPS : 1][RADIX];
     uint32_t bin_start[RADIX];          // exclusive scan of the tile's digit counts
     int32_t out_base[RADIX];            // global index of bin d's first element minus bin_start[d]
