@@ -42,6 +42,23 @@ __device__ __forceinline__ float exp_shared(float x) {
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(tm) << 23));
 }
 
+#if GSB_BLEND_TDONE
+// same sequence without the clamp: only evaluated results with power in [cut, 0] are used (identity there)
+__device__ __forceinline__ float exp_shared_inrange(float x) {
+    const float t = __fmul_rn(x, 1.44269504088896341f);
+    const float tm = __fadd_rn(t, 12582912.0f);
+    const float n = __fsub_rn(tm, 12582912.0f);
+    float r = __fmaf_rn(n, -0.693359375f, x);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    float p = __fmaf_rn(8.290082216262817e-3f, r, 4.1899293661117554e-2f);
+    p = __fmaf_rn(p, r, 1.6667647659778595e-1f);
+    p = __fmaf_rn(p, r, 4.9999138712882996e-1f);
+    p = __fmaf_rn(p, r, 9.999997019767761e-1f);
+    p = __fmaf_rn(p, r, 1.0f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(tm) << 23));
+}
+#endif
+
 // shared-memory loads by 32-bit shared-window address (one LDS each, immediate offsets, no generic-pointer arithmetic)
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
@@ -87,6 +104,9 @@ struct __align__(16) StagedRec {
 #ifndef GSB_BLEND_CHECK
 #define GSB_BLEND_CHECK 8  // records walked between two "is the whole warp done" votes (measured: 8 -> 0.673 ms, 16 -> 0.685, 32 -> 0.733)
 #endif
+#ifndef GSB_BLEND_TDONE
+#define GSB_BLEND_TDONE 0  // 1: a finished pixel is T == 0 (no separate flag in the walk); needs GSB_BLEND_PREDICATED
+#endif
 #ifndef GSB_BLEND_PREDICATED
 #define GSB_BLEND_PREDICATED 1
 #endif
@@ -115,7 +135,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
     __syncthreads();
 
     float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+#if GSB_BLEND_TDONE
+    if (!inside) T = 0.0f;
+#define BLEND_DONE (T == 0.0f)
+#else
     bool done = !inside;
+#define BLEND_DONE done
+#endif
     uint32_t used = 0;
     const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);  // < 64 KiB: fits the u16 list entries
 
@@ -132,7 +158,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
             s_mask[tid] = block_mask(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
         }
         __syncthreads();
-        if (!__all_sync(FULL, done)) {
+        if (!__all_sync(FULL, BLEND_DONE)) {
+#if GSB_BLEND_TDONE
+            const bool was_done = BLEND_DONE;
+#endif
             // compact this warp's survivors of the batch into a list of shared-memory addresses (one ballot per 32 records)
             uint32_t n = 0;
             for (uint32_t c = 0; c < cnt; c += 32) {
@@ -147,7 +176,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
             const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
             uint32_t fin_k = 0xffffffffu;
             for (uint32_t k0 = 0; k0 < n; k0 += GSB_BLEND_CHECK) {
-                if (__all_sync(FULL, done)) break;
+                if (__all_sync(FULL, BLEND_DONE)) break;
                 const uint32_t k1 = min(n, k0 + (uint32_t)GSB_BLEND_CHECK);
                 for (uint32_t k = k0; k < k1; k++) {
                     const uint32_t addr = lds_u16(list_sh + 2u * k);
@@ -158,11 +187,25 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
                     float power, alpha;
                     if (MODE == GSB_MODE_EXACT) {
                         power = ((a.z * dx) * dx + (b.x * dy) * dy) + (a.w * dx) * dy;  // :66 (pre-scaled conic)
+#if GSB_BLEND_TDONE
+                        alpha = fminf(0.99f, b.z * exp_shared_inrange(power));             // :77
+#else
                         alpha = fminf(0.99f, b.z * exp_shared(power));                     // :77
+#endif
                     } else {
                         power = fmaf(a.z * dx, dx, fmaf(b.x * dy, dy, (a.w * dx) * dy));
                         alpha = fminf(0.99f, b.z * __expf(power));
                     }
+#if GSB_BLEND_TDONE
+                    // A finished pixel carries T == 0 (a live one has T >= 1e-4): its test_T is 0, so it "finishes" again at
+                    // every record it would touch and never accumulates; fin_k keeps the FIRST such record.  A NaN power
+                    // fails both comparisons and is skipped, as in the oracle (its exp clamps NaN to exp(-87)).
+                    bool ok = (power <= 0.0f && power >= b.y) && !(alpha < 1.0f / 255.0f);  // :68-70, :78-80
+                    const float test_T = T * (1.0f - alpha);                               // :82
+                    const bool fin = ok && test_T < 0.0001f;                               // :83-85
+                    fin_k = fin ? min(fin_k, k) : fin_k;
+                    ok = ok && !fin;
+#else
                     // :68-70 and, below the Gaussian's cut, alpha < 1/255 (:78); a NaN power passes like in the shader
                     bool ok = !done && !(power > 0.0f || power < b.y) && !(alpha < 1.0f / 255.0f);  // :78-80
                     const float test_T = T * (1.0f - alpha);  // :82
@@ -171,6 +214,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
                         fin_k = k;
                         ok = false;
                     }
+#endif
 #if GSB_BLEND_PREDICATED
                     // select form: the products are computed unconditionally, only the four state updates are predicated
                     if (MODE == GSB_MODE_EXACT) {
@@ -184,7 +228,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
                         c1 = ok ? fmaf(gb.x, w, c1) : c1;
                         c2 = ok ? fmaf(gb.y, w, c2) : c2;
                     }
+#if GSB_BLEND_TDONE
+                    T = fin ? 0.0f : (ok ? test_T : T);  // :88, and the break
+#else
                     T = ok ? test_T : T;  // :88
+#endif
 #else
                     if (ok) {
                         if (MODE == GSB_MODE_EXACT) {
@@ -202,10 +250,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
 #endif
                 }
             }
+#if GSB_BLEND_TDONE
+            if (!was_done && fin_k != 0xffffffffu) used = base - range.x + (s_list[warp][fin_k] - rec_sh) / (uint32_t)sizeof(StagedRec) + 1;
+            else if (!BLEND_DONE) used = base - range.x + cnt;
+#else
             if (fin_k != 0xffffffffu) used = base - range.x + (s_list[warp][fin_k] - rec_sh) / (uint32_t)sizeof(StagedRec) + 1;
             else if (!done) used = base - range.x + cnt;
+#endif
         }
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(BLEND_DONE)) break;
     }
 
     if (inside) {
