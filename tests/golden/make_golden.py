@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generates tests/golden/c1_small.npz from the CPU oracle.
+"""Generates tests/golden/*.npz (c1_small, c1_odd) from the CPU oracle.
 
 The reference (shg8/3DGS.cpp) has no golden vectors and cannot be run here (PARITY UNPINNED), so these
 fixtures pin the ORACLE itself against accidental change and give the GPU tests a committed target:
@@ -19,22 +19,38 @@ sys.path.insert(0, str(ROOT / "oracle"))
 import gs_b200 as g  # noqa: E402
 import oracle as o  # noqa: E402
 
-SEED, N, W, H = 42, 2000, 160, 120
+# name: seed, n, width, height, camera position, camera quaternion (w, x, y, z), fov, synth params
+FIXTURES = {
+    "c1_small": dict(seed=42, n=2000, w=160, h=120, pos=[0, 0, 5], quat=[1, 0, 0, 0], fov=45.0, synth={}),
+    # odd image size (partial tiles on both edges), off-axis rotated camera inside the cloud (near-plane culls,
+    # Gaussians straddling the image border), large anisotropic splats (AABB clamping, long tile runs)
+    "c1_odd": dict(seed=7, n=1500, w=203, h=117, pos=[0.7, -0.4, 2.2], quat=[0.9689124, 0.0, 0.2474040, 0.0], fov=70.0,
+                   synth=dict(log_scale_min=-4.0, log_scale_max=-0.7)),
+}
 
 
-def main():
-    vtx = g.activate_records(g.synth_records(SEED, N))
-    u = g.uniforms_from_camera([0, 0, 5], [1, 0, 0, 0], 45.0, 0.1, 1000.0, W, H)
+def make(name):
+    fx = FIXTURES[name]
+    p = g.synth_params(**fx["synth"]) if fx["synth"] else None
+    rec = g.synth_records(fx["seed"], fx["n"], p) if p is not None else g.synth_records(fx["seed"], fx["n"])
+    vtx = g.activate_records(rec)
+    u = g.uniforms_from_camera(fx["pos"], fx["quat"], fx["fov"], 0.1, 1000.0, fx["w"], fx["h"])
     cov = o.cov3d(vtx)
     f0 = o.render_frame(vtx, cov, u)
     o.set_exp_mode(1)
     f1 = o.render_frame(vtx, cov, u)
     o.set_exp_mode(0)
-    np.savez_compressed(Path(__file__).with_name("c1_small.npz"), seed=SEED, n=N, width=W, height=H,
+    out = Path(__file__).with_name(name + ".npz")
+    np.savez_compressed(out, seed=fx["seed"], n=fx["n"], width=fx["w"], height=fx["h"],
                         uniforms=np.frombuffer(bytes(u), np.uint8), m=f1["m"], tiles=f1["tiles"], keys=f1["keys"],
                         vals=f1["vals"], ranges=f1["ranges"], rgba_exp_shared=f1["rgba"], rgba_exp_libm=f0["rgba"],
                         cov3d=cov)
-    print("wrote", Path(__file__).with_name("c1_small.npz"), "M =", f1["m"])
+    print("wrote", out, "M =", f1["m"])
+
+
+def main():
+    for name in (sys.argv[1:] or FIXTURES):
+        make(name)
 
 
 if __name__ == "__main__":

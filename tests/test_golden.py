@@ -1,23 +1,30 @@
 """Committed golden fixtures (tests/golden/make_golden.py).  CPU: the oracle still reproduces them.
 GPU: the CUDA path reproduces them bit for bit."""
+import sys
 from pathlib import Path
 
 import numpy as np
 import pytest
 
-GOLD = Path(__file__).parent / "golden" / "c1_small.npz"
+GOLD_DIR = Path(__file__).parent / "golden"
+sys.path.insert(0, str(GOLD_DIR))
+from make_golden import FIXTURES  # noqa: E402  (the fixture specs: seeds, cameras, synth parameters)
 
 
-def load(gs):
-    z = np.load(GOLD)
-    vtx = gs.activate_records(gs.synth_records(int(z["seed"]), int(z["n"])))
+def load(gs, name="c1_small"):
+    z = np.load(GOLD_DIR / f"{name}.npz")
+    fx = FIXTURES[name]
+    rec = gs.synth_records(int(z["seed"]), int(z["n"]), gs.synth_params(**fx["synth"])) if fx["synth"] else gs.synth_records(int(z["seed"]), int(z["n"]))
+    vtx = gs.activate_records(rec)
     u = gs.Uniforms.from_buffer_copy(z["uniforms"].tobytes())
     return z, vtx, u
 
 
-def test_oracle_reproduces_golden(gs, oracle):
-    z, vtx, u = load(gs)
-    assert bytes(gs.uniforms_from_camera([0, 0, 5], [1, 0, 0, 0], 45.0, 0.1, 1000.0, int(z["width"]), int(z["height"]))) == bytes(u)
+@pytest.mark.parametrize("name", sorted(FIXTURES))
+def test_oracle_reproduces_golden(gs, oracle, name):
+    z, vtx, u = load(gs, name)
+    fx = FIXTURES[name]
+    assert bytes(gs.uniforms_from_camera(fx["pos"], fx["quat"], fx["fov"], 0.1, 1000.0, int(z["width"]), int(z["height"]))) == bytes(u)
     cov = oracle.cov3d(vtx)
     assert np.array_equal(cov, z["cov3d"])
     oracle.set_exp_mode(1)
