@@ -17,6 +17,21 @@ using namespace gsb;
 namespace {
 thread_local std::string g_create_error;
 
+// Captured CUDA graph of the "middle" of a frame (depth sort, key emission, tile sort: 9-10 kernels whose arguments do
+// not depend on the camera).  Replaces recordRenderCommandBuffer's pre-recorded command buffer (src/Renderer.cpp:532-717).
+struct MiddleKey {
+    uint32_t tiles_x = 0, num_tiles = 0, nv_q = 0, m_q = 0, cull = 0;
+    uint64_t alloc_gen = 0;
+    bool operator==(const MiddleKey& o) const {
+        return tiles_x == o.tiles_x && num_tiles == o.num_tiles && nv_q == o.nv_q && m_q == o.m_q && cull == o.cull && alloc_gen == o.alloc_gen;
+    }
+};
+struct MiddleGraph {
+    MiddleKey key;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -63,9 +78,17 @@ struct gsb_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_sort[9] = {};  // instance sort: after hist, after each pass
     cudaEvent_t ev_done = nullptr;
+    cudaEvent_t ev_band[8] = {};  // host-output frames: blend band b finished (its D2H copy may start)
+    cudaStream_t copy_stream = nullptr;
     bool frame_pending = false;
     bool have_frame = false;
-    bool frame_debug = false;  // the last frame ran with gsb_set_debug on (its debug buffers and sorted keys exist)
+    bool frame_debug = false;   // the last frame ran with gsb_set_debug on (its debug buffers and sorted keys exist)
+    bool frame_timers = false;  // the last frame recorded the stage events (gsb_get_stats may read them)
+    bool use_graph = true;      // replay the sorts + key emission from a captured CUDA graph when timers and debug are off
+    uint64_t alloc_gen = 0;     // bumped by every (re)allocation a captured graph could point into
+    uint64_t graph_clock = 0;
+    uint32_t frames_since_epoch_clear = 0;
+    MiddleGraph graphs[4] = {};
     uint32_t m_hint = 0;
     uint32_t nv_hint = 0;
     uint32_t regrow_count = 0;
@@ -79,6 +102,7 @@ struct gsb_ctx {
     uint32_t* dbg_keys_unsorted = nullptr;
     uint32_t* dbg_vals_unsorted = nullptr;
     uint64_t dbg_m = 0;
+    unsigned long long* dbg_offsets = nullptr;  // N: k_emit's exclusive scan value per depth-sorted survivor
 };
 
 namespace {
@@ -121,13 +145,24 @@ int free_arena(gsb_ctx* ctx) {
     return GSB_OK;
 }
 
+void drop_graphs(gsb_ctx* ctx) {
+    for (auto& g : ctx->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = MiddleGraph{};
+    }
+}
+
 int ensure_sort_status(gsb_ctx* ctx, uint64_t items) {
     const uint32_t tiles = (uint32_t)((items + sort_tile_items() - 1) / sort_tile_items());
     if (tiles <= ctx->sort_status_tiles) return GSB_OK;
     dev_free(ctx->sort_status);
     ctx->sort_status_tiles = 0;
+    ctx->alloc_gen++;
     CK(dev_alloc(&ctx->sort_status, (size_t)tiles * 256));
-    CK(cudaMemset(ctx->sort_status, 0, (size_t)tiles * 256 * sizeof(unsigned long long)));
+    // Epoch tag 0 = "never published".  The frames run on ctx->stream (non-blocking) or on a caller's stream, neither of
+    // which is ordered against the legacy default stream a plain cudaMemset uses: clear on our stream and wait.
+    CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)tiles * 256 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->sort_status_tiles = tiles;
     return GSB_OK;
 }
@@ -140,6 +175,7 @@ int ensure_arena(gsb_ctx* ctx, uint64_t capacity) {
     dev_free(ctx->vals[0]);
     dev_free(ctx->vals[1]);
     ctx->capacity = 0;
+    ctx->alloc_gen++;
     CK(dev_alloc(&ctx->keys[0], capacity));
     CK(dev_alloc(&ctx->keys[1], capacity));
     CK(dev_alloc(&ctx->vals[0], capacity));
@@ -156,6 +192,15 @@ uint32_t bits_for(uint32_t count) {  // bits needed to represent 0 .. count-1
     return b;
 }
 
+// Grid sizes come from the previous frame's counts; quantised to powers of two so that consecutive frames launch the
+// same grids (any grid size is correct: every count-dependent kernel is a ticket / grid-stride loop) and a captured
+// graph stays valid while the camera moves.
+uint32_t quantise_hint(uint64_t hint) {
+    uint64_t q = 4096;
+    while (q < hint && q < (1ull << 31)) q <<= 1;
+    return (uint32_t)q;
+}
+
 size_t bytes_per_pixel(int fmt) { return fmt == GSB_FORMAT_RGBA32F ? 16 : 4; }
 
 int wait_frame(gsb_ctx* ctx) {
@@ -168,50 +213,45 @@ int wait_frame(gsb_ctx* ctx) {
     return GSB_OK;
 }
 
-// Enqueue one frame on `stream`; out_dev is device memory.
-int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out_dev, size_t pitch, int fmt,
-                  cudaStream_t stream) {
-    const uint32_t W = ubo->width, H = ubo->height;
-    const uint32_t tiles_x = (W + GSB_TILE - 1) / GSB_TILE, tiles_y = (H + GSB_TILE - 1) / GSB_TILE;
-    const uint32_t T = tiles_x * tiles_y;
-    if (T > ctx->ranges_tiles) {
-        dev_free(ctx->ranges);
-        CK(dev_alloc(&ctx->ranges, T));
-        ctx->ranges_tiles = T;
+__global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project_status, unsigned long long* __restrict__ emit_status,
+                             uint32_t chunks, uint2* __restrict__ ranges, uint32_t num_tiles) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    uint32_t* w = reinterpret_cast<uint32_t*>(ctl);
+    for (uint32_t k = i; k < sizeof(Control) / 4; k += stride) {
+        if (k == offsetof(Control, overflow_sticky) / 4) continue;  // reported (and cleared) by the host, not per frame
+        if (k == offsetof(Control, epoch) / 4) w[k] += 16u;          // fresh look-back tags for this frame's two sorts
+        else w[k] = 0u;
     }
-    const uint32_t n = (uint32_t)ctx->n;
-    const uint32_t chunks = (n + 255) / 256;
-
-    CK(cudaMemsetAsync(ctx->ctl, 0, sizeof(Control), stream));
-    CK(cudaMemsetAsync(ctx->project_status, 0, (size_t)std::max(chunks, 1u) * sizeof(uint32_t), stream));
-    CK(cudaMemsetAsync(ctx->emit_status, 0, (size_t)std::max(chunks, 1u) * sizeof(unsigned long long), stream));
-    if (ctx->epoch >= 0xffffff00u) {  // epoch wrap: clear the look-back tags once
-        CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
-        ctx->epoch = 8;
+    for (uint32_t k = i; k < chunks; k += stride) {
+        project_status[k] = 0u;
+        emit_status[k] = 0ull;
     }
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
+    for (uint32_t k = i; k < num_tiles; k += stride) ranges[k] = make_uint2(0xffffffffu, 0xffffffffu);  // tile_boundary's fillBuffer (Renderer.cpp:633)
+}
 
-    // ---- k_project: preprocess.comp + survivor compaction ----
-    ProjectParams pp{};
-    pp.pos_op = ctx->pos_op;
-    pp.cov_a = ctx->cov_a;
-    pp.cov_b = ctx->cov_b;
-    pp.sh = ctx->sh;
-    pp.n = n;
-    pp.ubo = *ubo;
-    pp.tile_row_begin = rb;
-    pp.tile_row_end = re;
-    pp.recs = ctx->recs;
-    pp.einfo = ctx->einfo;
-    pp.dkeys = ctx->dkeys[0];
-    pp.dvals = ctx->dvals[0];
-    pp.status = ctx->project_status;
-    pp.ctl = ctx->ctl;
-    pp.dbg_tiles = ctx->dbg_tiles;
-    pp.dbg_aabb = ctx->dbg_aabb;
-    CK(launch_project(pp, ctx->debug, stream));
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[1], stream));
+}  // namespace
 
+namespace gsb {
+cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, unsigned long long* emit_status, uint32_t chunks,
+                              uint2* ranges, uint32_t num_tiles, cudaStream_t s) {
+    const uint32_t work = std::max<uint32_t>(std::max(chunks, num_tiles), (uint32_t)(sizeof(Control) / 4));
+    const uint32_t blocks = std::min<uint32_t>((work + 255) / 256, 148u * 4u);
+    k_frame_init<<<blocks, 256, 0, s>>>(ctl, project_status, emit_status, chunks, ranges, num_tiles);
+    return cudaGetLastError();
+}
+}  // namespace gsb
+
+namespace {
+
+struct FramePlan {
+    uint32_t W, H, tiles_x, tiles_y, T, rb, re;
+    uint32_t nv_q, m_q, depth_passes, passes;
+    int fin;
+};
+
+// depth sort -> key emission -> tile sort: everything between k_project and k_blend.  No argument depends on the camera,
+// so the sequence is captured once per (frame size, grid sizes, allocation generation) and replayed.
+int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool events) {
     // ---- Gaussian-level Onesweep: the 32 depth bits (the reference's passes 0-3), N_v elements ----
     SortParams sa{};
     sa.keys[0] = ctx->dkeys[0];
@@ -220,11 +260,12 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     sa.vals[1] = ctx->dvals[1];
     sa.key_bytes = 4;
     sa.d_m = &ctx->ctl->num_visible;
-    sa.m_hint = ctx->nv_hint ? ctx->nv_hint : n;
+    sa.m_hint = fp.nv_q;
     sa.key_bits = 32;
     sa.status = ctx->sort_status;
     sa.status_tiles = ctx->sort_status_tiles;
-    sa.epoch_base = ctx->epoch;
+    sa.d_epoch = &ctx->ctl->epoch;
+    sa.epoch_base = 0;
     sa.sc = &ctx->ctl->sort_depth;
     sa.num_sms = ctx->num_sms;
     sa.events = nullptr;
@@ -233,14 +274,14 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     uint32_t depth_passes = 0;
     CK(launch_sort(sa, &depth_passes, stream));
     const int fin_a = depth_passes & 1;
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[2], stream));
+    if (events) CK(cudaEventRecord(ctx->ev[2], stream));
 
     // ---- k_emit: scan of tile counts + (tile id, payload) emission in depth order ----
     EmitParams ep{};
     ep.sorted_cid = ctx->dvals[fin_a];
     ep.einfo = ctx->einfo;
-    ep.nv_hint = sa.m_hint;
-    ep.tiles_x = tiles_x;
+    ep.nv_hint = fp.nv_q;
+    ep.tiles_x = fp.tiles_x;
     ep.keys = ctx->keys[0];
     ep.vals = ctx->vals[0];
     ep.capacity = (uint32_t)ctx->capacity;
@@ -249,8 +290,9 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     ep.num_sms = ctx->num_sms;
     ep.recs = ctx->recs;
     ep.cull = ctx->tile_cull ? 1 : 0;
+    ep.dbg_offsets = ctx->debug ? ctx->dbg_offsets : nullptr;
     CK(launch_emit(ep, stream));
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[3], stream));
+    if (events) CK(cudaEventRecord(ctx->ev[3], stream));
 
     if (ctx->debug) {  // keep the emitted (not yet tile-sorted) pairs: the reference's sort buffers after its pass 3
         CK(cudaStreamSynchronize(stream));
@@ -273,56 +315,178 @@ int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     sp.vals[1] = ctx->vals[1];
     sp.key_bytes = 4;
     sp.d_m = &ctx->ctl->num_instances;
-    sp.m_hint = ctx->m_hint ? ctx->m_hint : (uint32_t)std::min<uint64_t>(ctx->capacity, 4u * 1024 * 1024);
-    sp.key_bits = bits_for(T);
+    sp.m_hint = fp.m_q;
+    sp.key_bits = bits_for(fp.T);
     sp.status = ctx->sort_status;
     sp.status_tiles = ctx->sort_status_tiles;
-    sp.epoch_base = ctx->epoch + 4;
-    ctx->epoch += 8;
+    sp.d_epoch = &ctx->ctl->epoch;
+    sp.epoch_base = 4;
     sp.sc = &ctx->ctl->sort_tile;
     sp.num_sms = ctx->num_sms;
-    sp.events = ctx->timers ? ctx->ev_sort : nullptr;
+    sp.events = events ? ctx->ev_sort : nullptr;
     sp.ranges = ctx->ranges;  // the last pass writes the tile ranges (tile_boundary.comp fused)
     sp.discard_sorted_keys = !ctx->debug;  // only gsb_debug_download(GSB_BUF_KEYS) reads them; the blend uses vals + ranges
-    CK(launch_ranges_init(ctx->ranges, T, stream));
     uint32_t passes = 0;
     CK(launch_sort(sp, &passes, stream));
-    const int fin = passes & 1;
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[4], stream));
-
+    if (events) CK(cudaEventRecord(ctx->ev[4], stream));
     if (passes == 0) CK(launch_ranges_single_tile(sp.d_m, ctx->ranges, stream));  // one tile: nothing to sort
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[5], stream));
+    if (events) CK(cudaEventRecord(ctx->ev[5], stream));
+    if (depth_passes != fp.depth_passes || passes != fp.passes) return fail(ctx, GSB_ERR_CUDA, "internal: pass count mismatch");
+    return GSB_OK;
+}
 
+// The same sequence replayed from a captured graph (4-entry LRU over MiddleKey).
+int launch_middle_graph(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) {
+    MiddleKey key;
+    key.tiles_x = fp.tiles_x;
+    key.num_tiles = fp.T;
+    key.nv_q = fp.nv_q;
+    key.m_q = fp.m_q;
+    key.cull = ctx->tile_cull ? 1u : 0u;
+    key.alloc_gen = ctx->alloc_gen;
+    MiddleGraph* slot = nullptr;
+    for (auto& g : ctx->graphs)
+        if (g.exec && g.key == key) slot = &g;
+    if (!slot) {
+        slot = &ctx->graphs[0];
+        for (auto& g : ctx->graphs)
+            if (!g.exec || (slot->exec && g.last_use < slot->last_use)) slot = &g;
+        if (slot->exec) cudaGraphExecDestroy(slot->exec);
+        *slot = MiddleGraph{};
+        // capture on the context's own stream (a caller's stream may be in use by its owner); the graph is launched on `stream`
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_middle(ctx, fp, ctx->stream, false);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != GSB_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) return fail(ctx, GSB_ERR_CUDA, "cudaStreamEndCapture", e);
+        e = cudaGraphInstantiate(&slot->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            slot->exec = nullptr;
+            return fail(ctx, GSB_ERR_CUDA, "cudaGraphInstantiate", e);
+        }
+        slot->key = key;
+    }
+    slot->last_use = ++ctx->graph_clock;
+    CK(cudaGraphLaunch(slot->exec, stream));
+    return GSB_OK;
+}
+
+// frame start + k_project + middle.  After this the tile ranges and sorted payloads of the frame are in flight on `stream`.
+int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, cudaStream_t stream, FramePlan* out) {
+    FramePlan fp{};
+    fp.W = ubo->width;
+    fp.H = ubo->height;
+    fp.tiles_x = (fp.W + GSB_TILE - 1) / GSB_TILE;
+    fp.tiles_y = (fp.H + GSB_TILE - 1) / GSB_TILE;
+    fp.T = fp.tiles_x * fp.tiles_y;
+    fp.rb = rb;
+    fp.re = re;
+    if (fp.T > ctx->ranges_tiles) {
+        dev_free(ctx->ranges);
+        ctx->alloc_gen++;
+        CK(dev_alloc(&ctx->ranges, fp.T));
+        ctx->ranges_tiles = fp.T;
+    }
+    const uint32_t n = (uint32_t)ctx->n;
+    const uint32_t chunks = (n + 255) / 256;
+    fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : n), quantise_hint(n));
+    fp.m_q = quantise_hint(ctx->m_hint ? ctx->m_hint : std::min<uint64_t>(ctx->capacity, 4u * 1024 * 1024));
+    fp.depth_passes = 4;
+    fp.passes = (bits_for(fp.T) + 7) / 8;
+    fp.fin = (int)(fp.passes & 1);
+
+    if (++ctx->frames_since_epoch_clear >= (1u << 27)) {  // epoch wrap (2^32 / 16 frames): clear the look-back tags once
+        CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
+        CK(cudaMemsetAsync(&ctx->ctl->epoch, 0, sizeof(uint32_t), stream));
+        ctx->frames_since_epoch_clear = 0;
+    }
+    const bool timers = ctx->timers;
+    CK(launch_frame_init(ctx->ctl, ctx->project_status, ctx->emit_status, std::max(chunks, 1u), ctx->ranges, fp.T, stream));
+    if (timers) CK(cudaEventRecord(ctx->ev[0], stream));
+
+    // ---- k_project: preprocess.comp + survivor compaction ----
+    ProjectParams pp{};
+    pp.pos_op = ctx->pos_op;
+    pp.cov_a = ctx->cov_a;
+    pp.cov_b = ctx->cov_b;
+    pp.sh = ctx->sh;
+    pp.n = n;
+    pp.ubo = *ubo;
+    pp.tile_row_begin = rb;
+    pp.tile_row_end = re;
+    pp.recs = ctx->recs;
+    pp.einfo = ctx->einfo;
+    pp.dkeys = ctx->dkeys[0];
+    pp.dvals = ctx->dvals[0];
+    pp.status = ctx->project_status;
+    pp.ctl = ctx->ctl;
+    pp.dbg_tiles = ctx->dbg_tiles;
+    pp.dbg_aabb = ctx->dbg_aabb;
+    CK(launch_project(pp, ctx->debug, stream));
+    if (timers) CK(cudaEventRecord(ctx->ev[1], stream));
+
+    int rc;
+    if (ctx->use_graph && !timers && !ctx->debug) rc = launch_middle_graph(ctx, fp, stream);
+    else rc = enqueue_middle(ctx, fp, stream, timers);
+    if (rc != GSB_OK) return rc;
+    *out = fp;
+    return GSB_OK;
+}
+
+// k_blend over tile rows [b0, b1) of the frame; `band_out` is the first pixel row of the frame's band [fp.rb, fp.re).
+int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, void* band_out, size_t pitch, int fmt,
+                  cudaStream_t stream) {
     BlendParams bp{};
     bp.recs = ctx->recs;
-    bp.vals = ctx->vals[fin];
+    bp.vals = ctx->vals[fp.fin];
     bp.ranges = ctx->ranges;
-    bp.width = W;
-    bp.height = H;
-    bp.tiles_x = tiles_x;
-    bp.tile_row_begin = rb;
-    bp.tile_row_end = re;
-    bp.out = out_dev;
+    bp.width = fp.W;
+    bp.height = fp.H;
+    bp.tiles_x = fp.tiles_x;
+    bp.tile_row_begin = b0;
+    bp.tile_row_end = b1;
+    bp.out = static_cast<unsigned char*>(band_out) + (size_t)(b0 - fp.rb) * GSB_TILE * pitch;
     bp.row_pitch_bytes = pitch;
     bp.format = fmt;
     bp.mode = ctx->mode;
     bp.ctl = ctx->ctl;
     CK(launch_blend(bp, stream));
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[6], stream));
+    return GSB_OK;
+}
 
+// stats copy + completion event; latches what gsb_get_stats / gsb_debug_download may read about this frame
+int enqueue_tail(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) {
+    if (ctx->timers) CK(cudaEventRecord(ctx->ev[6], stream));
     CK(cudaMemcpyAsync(ctx->ctl_host, ctx->ctl, offsetof(Control, sort_depth), cudaMemcpyDeviceToHost, stream));
     CK(cudaEventRecord(ctx->ev_done, stream));
     ctx->frame_pending = true;
     ctx->have_frame = true;
     ctx->frame_debug = ctx->debug;
-    ctx->last_w = W;
-    ctx->last_h = H;
-    ctx->last_tiles_x = tiles_x;
-    ctx->last_tiles_y = tiles_y;
-    ctx->last_passes = passes;
-    ctx->last_depth_passes = depth_passes;
-    ctx->last_final = (uint32_t)fin;
+    ctx->frame_timers = ctx->timers;
+    ctx->last_w = fp.W;
+    ctx->last_h = fp.H;
+    ctx->last_tiles_x = fp.tiles_x;
+    ctx->last_tiles_y = fp.tiles_y;
+    ctx->last_passes = fp.passes;
+    ctx->last_depth_passes = fp.depth_passes;
+    ctx->last_final = (uint32_t)fp.fin;
     return GSB_OK;
+}
+
+// Enqueue one whole frame on `stream`; out_dev is device memory.
+int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out_dev, size_t pitch, int fmt,
+                  cudaStream_t stream) {
+    FramePlan fp{};
+    int rc = enqueue_front(ctx, ubo, rb, re, stream, &fp);
+    if (rc != GSB_OK) return rc;
+    rc = enqueue_blend(ctx, fp, rb, re, out_dev, pitch, fmt, stream);
+    if (rc != GSB_OK) return rc;
+    return enqueue_tail(ctx, fp, stream);
 }
 
 int check_render_args(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t& rb, uint32_t& re, const void* out, size_t& pitch,
@@ -381,14 +545,25 @@ int gsb_create(int device, gsb_ctx** out) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
-    if (prop.major < 10) {
-        g_create_error = "libgsb200 is built for sm_100a (B200) only";
+    // The library carries sm_100a SASS only (arch-specific, no forward-compatible PTX): any other device would pass
+    // here and fail at its first launch with "no kernel image".  Probe a kernel image instead of trusting major/minor.
+    cudaFuncAttributes fa;
+    if (prop.major != 10 || prop.minor != 0 || cudaFuncGetAttributes(&fa, k_frame_init) != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = "libgsb200 is built for sm_100a (B200, compute capability 10.0) only; device is sm_" +
+                         std::to_string(prop.major) + std::to_string(prop.minor);
         gsb_destroy(ctx);
         return GSB_ERR_NO_DEVICE;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    if ((e = sort_prepare()) != cudaSuccess) return bail("sort_prepare", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& ev : ctx->ev_band)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = dev_alloc(&ctx->ctl, 1)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMemset(ctx->ctl, 0, sizeof(Control))) != cudaSuccess) return bail("cudaMemset", e);  // epoch and overflow_sticky start at 0
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail("cudaDeviceSynchronize", e);
     if ((e = cudaMallocHost(reinterpret_cast<void**>(&ctx->ctl_host), sizeof(Control))) != cudaSuccess) return bail("cudaMallocHost", e);
     memset(ctx->ctl_host, 0, sizeof(Control));
     for (auto& ev : ctx->ev)
@@ -405,6 +580,11 @@ void gsb_destroy(gsb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
+    drop_graphs(ctx);
+    dev_free(ctx->dbg_offsets);
+    for (auto& ev : ctx->ev_band)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     dev_free(ctx->pos_op);
     dev_free(ctx->cov_a);
     dev_free(ctx->cov_b);
@@ -457,7 +637,10 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     dev_free(ctx->emit_status);
     dev_free(ctx->dbg_tiles);
     dev_free(ctx->dbg_aabb);
+    dev_free(ctx->dbg_offsets);
     ctx->n = 0;
+    ctx->alloc_gen++;
+    drop_graphs(ctx);
     CK(dev_alloc(&ctx->pos_op, n));
     CK(dev_alloc(&ctx->cov_a, n));
     CK(dev_alloc(&ctx->cov_b, n));
@@ -473,6 +656,7 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     if (ctx->debug) {
         CK(dev_alloc(&ctx->dbg_tiles, n));
         CK(dev_alloc(&ctx->dbg_aabb, n));
+        CK(dev_alloc(&ctx->dbg_offsets, n));
     }
     // stream the AoS records through a bounded staging buffer (C5: 50 M x 240 B = 12 GB on the host)
     const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), 1u << 20);
@@ -529,8 +713,31 @@ int gsb_set_debug(gsb_ctx* ctx, int debug) {
     if (ctx->debug && ctx->n && !ctx->dbg_tiles) {
         CK(dev_alloc(&ctx->dbg_tiles, ctx->n));
         CK(dev_alloc(&ctx->dbg_aabb, ctx->n));
+        CK(dev_alloc(&ctx->dbg_offsets, ctx->n));
     }
     return GSB_OK;
+}
+
+int gsb_set_graph(gsb_ctx* ctx, int enabled) {
+    if (!ctx) return GSB_ERR_INVALID;
+    ctx->use_graph = enabled != 0;
+    return GSB_OK;
+}
+
+int gsb_host_alloc(void** out, size_t bytes) {
+    if (!out) return GSB_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? GSB_ERR_OOM : GSB_ERR_CUDA;
+    }
+    return GSB_OK;
+}
+
+void gsb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 int gsb_set_tile_cull(gsb_ctx* ctx, int enabled) {
@@ -561,6 +768,7 @@ int gsb_render_async(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_
     if (ctx->frame_pending && cudaEventQuery(ctx->ev_done) == cudaSuccess) {  // opportunistic hint refresh
         ctx->frame_pending = false;
         ctx->m_hint = ctx->ctl_host->num_instances;
+        ctx->nv_hint = ctx->ctl_host->num_visible;
     }
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     return enqueue_frame(ctx, ubo, rb, re, out_device, pitch, fmt, s);
@@ -590,8 +798,29 @@ int gsb_render(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
         dev_out = ctx->fb;
         dev_pitch = tight;
     }
+    // Host output: the blend runs in up to 8 row bands and every finished band is copied device -> host on a second stream
+    // while the next bands are still blending, so only the last band's copy is exposed (17.9 MB BGRA8 at 3200x1400 is
+    // ~0.33 ms of PCIe time, the blend ~0.65 ms).  Pinned `out` (gsb_host_alloc) makes the copies truly asynchronous.
+    const uint32_t band_rows = re - rb;
+    const uint32_t nb = out_mem == GSB_MEM_HOST ? std::min<uint32_t>(8u, band_rows) : 1u;
     for (int attempt = 0;; attempt++) {
-        rc = enqueue_frame(ctx, ubo, rb, re, dev_out, dev_pitch, fmt, s);
+        FramePlan fp{};
+        rc = enqueue_front(ctx, ubo, rb, re, s, &fp);
+        if (rc != GSB_OK) return rc;
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint32_t b0 = rb + (uint32_t)((uint64_t)band_rows * b / nb), b1 = rb + (uint32_t)((uint64_t)band_rows * (b + 1) / nb);
+            rc = enqueue_blend(ctx, fp, b0, b1, dev_out, dev_pitch, fmt, s);
+            if (rc != GSB_OK) return rc;
+            if (out_mem == GSB_MEM_HOST) {
+                const uint32_t y0 = (b0 - rb) * GSB_TILE, y1 = std::min(H, b1 * GSB_TILE) - rb * GSB_TILE;
+                CK(cudaEventRecord(ctx->ev_band[b], s));
+                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
+                CK(cudaMemcpy2DAsync(static_cast<unsigned char*>(out) + (size_t)y0 * pitch, pitch,
+                                     static_cast<unsigned char*>(dev_out) + (size_t)y0 * dev_pitch, dev_pitch, tight, y1 - y0,
+                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+            }
+        }
+        rc = enqueue_tail(ctx, fp, s);
         if (rc != GSB_OK) return rc;
         rc = wait_frame(ctx);
         if (rc != GSB_OK) return rc;
@@ -599,14 +828,13 @@ int gsb_render(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
         // arena overflow: grow like the reference's sortBufferSizeMultiplier retry (Renderer.cpp:541-563)
         if (attempt >= 3) return fail(ctx, GSB_ERR_OVERFLOW, "instance arena overflow persists after regrow");
         const uint64_t want = ctx->ctl_host->instances_total + ctx->ctl_host->instances_total / 4 + 4096;
+        if (out_mem == GSB_MEM_HOST) CK(cudaStreamSynchronize(ctx->copy_stream));
         rc = ensure_arena(ctx, want);
         if (rc != GSB_OK) return rc;
+        CK(cudaMemsetAsync(&ctx->ctl->overflow_sticky, 0, sizeof(uint32_t), s));  // this overflow is being handled right here
         ctx->regrow_count++;
     }
-    if (out_mem == GSB_MEM_HOST) {
-        CK(cudaMemcpy2DAsync(out, pitch, dev_out, dev_pitch, tight, rows, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-    }
+    if (out_mem == GSB_MEM_HOST) CK(cudaStreamSynchronize(ctx->copy_stream));
     return GSB_OK;
 }
 
@@ -631,7 +859,7 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
     out->sort_passes = ctx->last_passes;
     out->sort_depth_passes = ctx->last_depth_passes;
     out->regrow_count = ctx->regrow_count;
-    if (ctx->timers) {
+    if (ctx->frame_timers) {  // latched per frame: toggling gsb_set_timers between frames must not read stale events
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
         out->preprocess_ms = ms;  // k_project
@@ -657,7 +885,14 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]));
         out->frame_ms = ms;
     }
-    if (c->overflow) return fail(ctx, GSB_ERR_OVERFLOW, "last frame overflowed the instance arena (gsb_render regrows; gsb_render_async does not)");
+    if (c->overflow || c->overflow_sticky) {
+        // sticky: set by ANY frame since the last report (pipelined gsb_render_async frames overwrite the per-frame flag)
+        CK(cudaMemsetAsync(&ctx->ctl->overflow_sticky, 0, sizeof(uint32_t), ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->ctl_host->overflow_sticky = 0;
+        return fail(ctx, GSB_ERR_OVERFLOW, c->overflow ? "last frame overflowed the instance arena (gsb_render regrows; gsb_render_async does not)"
+                                                       : "an earlier gsb_render_async frame overflowed the instance arena (its image is incomplete)");
+    }
     return GSB_OK;
 }
 
@@ -677,6 +912,8 @@ size_t gsb_debug_size(gsb_ctx* ctx, gsb_buffer which) {
         case GSB_BUF_VALS_UNSORTED:
         case GSB_BUF_VALS_SORTED: return (size_t)m * 4;
         case GSB_BUF_TILE_BOUNDARY: return (size_t)ctx->last_tiles_x * ctx->last_tiles_y * 8;
+        case GSB_BUF_DEPTH_ORDER: return (size_t)ctx->ctl_host->num_visible * 4;
+        case GSB_BUF_EMIT_OFFSETS: return (size_t)ctx->ctl_host->num_visible * 8;
         default: return 0;
     }
 }
@@ -783,6 +1020,22 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
             }
             return GSB_OK;
         }
+        case GSB_BUF_DEPTH_ORDER: {  // the Gaussian-level sort's output: survivors in (depth bits, index) order, as Gaussian indices
+            std::vector<float4> recs((size_t)nv * 3);
+            std::vector<uint32_t> cid(nv);
+            if (nv) {
+                CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(cid.data(), ctx->dvals[ctx->last_depth_passes & 1], (size_t)nv * 4, cudaMemcpyDeviceToHost));
+            }
+            for (uint32_t j = 0; j < nv; j++) {
+                if (cid[j] >= nv) return fail(ctx, GSB_ERR_CUDA, "corrupt depth order");
+                memcpy(static_cast<uint32_t*>(dst) + j, &recs[(size_t)cid[j] * 3 + 2].w, 4);
+            }
+            return GSB_OK;
+        }
+        case GSB_BUF_EMIT_OFFSETS:  // k_emit's device scan: exclusive instance offset of each depth-sorted survivor
+            if (nv) CK(cudaMemcpy(dst, ctx->dbg_offsets, (size_t)nv * 8, cudaMemcpyDeviceToHost));
+            return GSB_OK;
         case GSB_BUF_TILE_BOUNDARY: {  // device encoding (start, ~end), untouched = all ones -> the reference's (start, end) / (0, 0)
             CK(cudaMemcpy(dst, ctx->ranges, need, cudaMemcpyDeviceToHost));
             uint32_t* o = static_cast<uint32_t*>(dst);
@@ -812,7 +1065,7 @@ static int sort_pairs_impl(gsb_ctx* ctx, void* keys, uint32_t* vals, void* keys_
     unsigned long long* status = nullptr;
     CK(dev_alloc(&status, (size_t)tiles * 256));
     cudaError_t e = cudaMemsetAsync(status, 0, (size_t)tiles * 256 * 8, s);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->ctl, 0, sizeof(Control), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(&ctx->ctl->sort_tile, 0, sizeof(SortCtl), s);  // not the whole block: epoch / overflow_sticky persist
     const uint32_t m32 = (uint32_t)m;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&ctx->ctl->num_instances, &m32, 4, cudaMemcpyHostToDevice, s);
     SortParams sp{};
@@ -826,6 +1079,7 @@ static int sort_pairs_impl(gsb_ctx* ctx, void* keys, uint32_t* vals, void* keys_
     sp.key_bits = key_bits;
     sp.status = status;
     sp.status_tiles = tiles;
+    sp.d_epoch = nullptr;
     sp.epoch_base = 8;
     sp.sc = &ctx->ctl->sort_tile;
     sp.num_sms = ctx->num_sms;

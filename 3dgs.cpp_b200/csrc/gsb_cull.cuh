@@ -14,14 +14,16 @@
 
 namespace gsb {
 
-constexpr float POWER_CUT = -5.55f;  // alpha = opacity * exp(power) <= exp(-5.55) < 1/255 because opacity <= 1
+constexpr float POWER_CUT = -5.55f;  // for opacity <= 1: alpha = opacity * exp(power) <= exp(-5.55) < 1/255 (documentation only)
 
 // Per-Gaussian version of the same cut: power < power_cut(opacity) implies opacity * exp(power) < 1/255 in the
 // kernel's arithmetic (the 1e-3 margin dwarfs the error of __logf, of the shared-definition exp and of the final
-// multiply).  Always >= POWER_CUT's companion -log(255) - 1e-3 = -5.5423 since opacity <= 1; clamped to <= 0.
+// multiply).  For opacity <= 1 (what GSScene::load produces) it is >= -log(255) - 1e-3 = -5.5423; gsb_scene_upload
+// does not validate opacities, so the bound is NOT clamped at POWER_CUT: for opacity > 1 it is simply lower (down to
+// the exp's own clamp at -87), and the kernel keeps every pair render.comp:77-80 would blend.  Clamped to <= 0.
 __device__ __forceinline__ float power_cut(float opacity) {
     const float c = -__logf(255.0f * opacity) - 1e-3f;  // opacity <= 0 / NaN -> +inf / NaN -> clamped to 0 below
-    return fminf(fmaxf(c, POWER_CUT), 0.0f);
+    return fminf(fmaxf(c, -87.0f), 0.0f);
 }
 
 // Minimum over [lo, hi] of the 1-D quadratic  q(t) = a t^2 + 2 b t + c  (a > 0, inv_a ~ 1/a).

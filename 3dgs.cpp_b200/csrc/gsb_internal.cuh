@@ -31,14 +31,16 @@ struct SortCtl {
     uint32_t hist[8][256];  // global digit histograms
 };
 
-// ---- per-frame control block (device memory, zeroed by one memset at frame start) ----
+// ---- per-frame control block (device memory, zeroed by k_frame_init at frame start, except overflow_sticky) ----
 struct Control {
     uint32_t project_ticket;   // chunk tickets of k_project
     uint32_t emit_ticket;      // chunk tickets of k_emit
     uint32_t num_visible;      // N_v
     uint32_t num_instances;    // M clamped to the arena capacity
-    uint32_t overflow;         // 1 if M_total > capacity
-    uint32_t pad0[3];
+    uint32_t overflow;         // 1 if M_total > capacity in THIS frame
+    uint32_t overflow_sticky;  // OR of `overflow` over every frame since it was last reported; survives k_frame_init
+    uint32_t epoch;            // look-back epoch of this frame's sorts: += 16 per frame by k_frame_init, never zeroed
+    uint32_t pad0;
     unsigned long long instances_total;  // unclamped M
     unsigned long long blend_consumed;
     unsigned long long candidates_total;  // AABB instances before tile culling (the reference's M)
@@ -79,6 +81,7 @@ struct EmitParams {
     int num_sms;
     const float4* recs;          // blend records (centre + conic) for the optional instance culling
     int cull;                    // gsb_set_tile_cull
+    unsigned long long* dbg_offsets;  // debug (may be null): exclusive instance offset of each depth-sorted survivor
 };
 
 cudaError_t launch_cov3d(const float* vtx_aos, uint64_t count, uint64_t dst_offset, float4* pos_op,
@@ -95,7 +98,8 @@ struct SortParams {
     uint32_t key_bits;
     unsigned long long* status;  // epoch-tagged look-back words [tiles][256]
     uint32_t status_tiles;     // capacity of status in tiles
-    uint32_t epoch_base;       // unique per sort call; pass p uses epoch_base + p
+    const uint32_t* d_epoch;   // device word added to the epoch (the frame counter of Control; null = 0)
+    uint32_t epoch_base;       // pass p tags its look-back words with *d_epoch + epoch_base + p: unique per (frame, sort, pass)
     SortCtl* sc;               // must be zero on entry
     int num_sms;
     cudaEvent_t* events;       // optional: events[0] after the histogram, events[1 + p] after pass p
@@ -106,7 +110,11 @@ struct SortParams {
 cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s);
 uint32_t sort_tile_items();
 
-cudaError_t launch_ranges_init(uint2* ranges, uint32_t num_tiles, cudaStream_t s);  // (0xFFFFFFFF, 0xFFFFFFFF) = empty
+// One kernel instead of four memsets: zeroes the control block (keeping overflow_sticky) and the look-back words of
+// k_project / k_emit, and fills the tile ranges with (0xFFFFFFFF, 0xFFFFFFFF) = empty.
+cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, unsigned long long* emit_status, uint32_t chunks,
+                              uint2* ranges, uint32_t num_tiles, cudaStream_t s);
+cudaError_t sort_prepare();  // one-time function attributes (dynamic shared memory opt-in) of the Onesweep kernels
 cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaStream_t s);
 
 struct BlendParams {

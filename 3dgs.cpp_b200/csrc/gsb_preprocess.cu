@@ -431,12 +431,16 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
                         P.ctl->instances_total = total;
                         P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
                         P.ctl->overflow = total > P.capacity ? 1u : 0u;
+                        if (total > P.capacity) atomicOr(&P.ctl->overflow_sticky, 1u);  // survives the next frames' k_frame_init
                     }
                 }
             }
             }
             __syncthreads();
-            if (w0 == 0) base = s_base;
+            if (w0 == 0) {
+                base = s_base;
+                if (P.dbg_offsets != nullptr && j < nv) P.dbg_offsets[j] = base + off;  // the device scan, for gsb_debug_download
+            }
             for (uint32_t i = tid; i < w1 - w0; i += PRE_THREADS) {  // coalesced copy-out
                 const unsigned long long slot = base + w0 + i;
                 if (slot < P.capacity) {
@@ -668,11 +672,15 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_EMIT_MIN_BLOCKS) k_emit_cull(
                         P.ctl->instances_total = total;
                         P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
                         P.ctl->overflow = total > P.capacity ? 1u : 0u;
+                        if (total > P.capacity) atomicOr(&P.ctl->overflow_sticky, 1u);  // survives the next frames' k_frame_init
                     }
                 }
             }
             __syncthreads();
-            if (w0 == 0) base = s_base;
+            if (w0 == 0) {
+                base = s_base;
+                if (P.dbg_offsets != nullptr && j < nv) P.dbg_offsets[j] = base + off;  // the device scan, for gsb_debug_download
+            }
             for (uint32_t i = tid; i < w1 - w0; i += PRE_THREADS) {  // coalesced copy-out
                 const unsigned long long slot = base + w0 + i;
                 if (slot < P.capacity) {

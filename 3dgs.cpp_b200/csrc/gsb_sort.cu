@@ -214,7 +214,8 @@ template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
     k_onesweep_pass(const KeyT* __restrict__ kin, const uint32_t* __restrict__ vin, KeyT* __restrict__ kout,
                     uint32_t* __restrict__ vout, const uint32_t* __restrict__ d_m, SortCtl* sc, int pass,
-                    unsigned long long* status, uint32_t status_tiles, uint32_t epoch, uint2* __restrict__ ranges) {
+                    unsigned long long* status, uint32_t status_tiles, const uint32_t* __restrict__ d_epoch, uint32_t epoch_off,
+                    uint2* __restrict__ ranges) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PassSmem<KeyT>& S = *reinterpret_cast<PassSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,6 +223,8 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
     const uint32_t m = *d_m;
     uint32_t num_tiles = (m + SORT_TILE - 1) / SORT_TILE;
     if (num_tiles > status_tiles) num_tiles = status_tiles;  // host sizes status for the arena capacity
+    // the frame's epoch lives in device memory (bumped by k_frame_init) so a captured CUDA graph replays with fresh tags
+    const uint32_t epoch = (d_epoch ? *d_epoch : 0u) + epoch_off;
     const unsigned long long epoch_hi = (unsigned long long)epoch << 32;
 
     auto fetch = [&](int buf) {  // thread 0: take the next ticket and start its TMA loads into `buf`
@@ -476,11 +479,7 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         if (p.events && (e = cudaEventRecord(p.events[0], s)) != cudaSuccess) return e;
     }
-    const size_t smem = sizeof(PassSmem<KeyT>);
-    {
-        cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
+    const size_t smem = sizeof(PassSmem<KeyT>);  // opt-in done once by sort_prepare()
     uint32_t blocks = (hint + SORT_TILE - 1) / SORT_TILE;
     const uint32_t cap = (uint32_t)p.num_sms * ctas_per_sm<KeyT>();  // persistent CTAs; ticket loop: any grid size is correct
     if (blocks > cap) blocks = cap;
@@ -489,7 +488,7 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
         const int src = pass & 1, dst = src ^ 1;
         KeyT* kout = (pass + 1 == P && p.discard_sorted_keys) ? nullptr : keys[dst];
         k_onesweep_pass<KeyT><<<blocks, SORT_THREADS, smem, s>>>(keys[src], p.vals[src], kout, p.vals[dst], p.d_m, p.sc,
-                                                                 (int)pass, p.status, p.status_tiles, p.epoch_base + pass,
+                                                                 (int)pass, p.status, p.status_tiles, p.d_epoch, p.epoch_base + pass,
                                                                  pass + 1 == P ? p.ranges : nullptr);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -501,6 +500,14 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
 }  // namespace
 
 uint32_t sort_tile_items() { return SORT_TILE; }
+
+cudaError_t sort_prepare() {
+    cudaError_t e = cudaFuncSetAttribute(k_onesweep_pass<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PassSmem<uint32_t>));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_onesweep_pass<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(PassSmem<unsigned long long>));
+}
 
 cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s) {
     const uint32_t P = (p.key_bits + 7) / 8;
@@ -514,7 +521,7 @@ cudaError_t launch_sort(const SortParams& p, uint32_t* passes, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 // Tile ranges (replaces fillBuffer(0) + tile_boundary.comp:22-50, Renderer.cpp:633-652).
 // Encoding: ranges[t] = (start, ~end), untouched = (0xFFFFFFFF, 0xFFFFFFFF) = empty.  They are produced by the
-// last Onesweep pass of the instance sort (see k_onesweep_pass); this file only provides the 0xFF fill and the
+// last Onesweep pass of the instance sort (see k_onesweep_pass); the 0xFF fill is part of k_frame_init (gsb_api.cu); this file provides the
 // degenerate case of a single tile (no tile-id bits to sort, hence no pass).
 // ------------------------------------------------------------------------------------------
 namespace {
@@ -523,10 +530,6 @@ __global__ void k_ranges_single_tile(const uint32_t* __restrict__ d_m, uint2* __
     if (m) ranges[0] = make_uint2(0u, ~m);
 }
 }  // namespace
-
-cudaError_t launch_ranges_init(uint2* ranges, uint32_t num_tiles, cudaStream_t s) {
-    return cudaMemsetAsync(ranges, 0xFF, (size_t)num_tiles * sizeof(uint2), s);
-}
 
 cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaStream_t s) {
     k_ranges_single_tile<<<1, 1, 0, s>>>(d_m, ranges);

@@ -32,14 +32,14 @@ FORMAT_RGBA32F, FORMAT_RGBA8, FORMAT_BGRA8 = 0, 1, 2
 MODE_EXACT, MODE_FAST = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 (BUF_COV3D, BUF_ATTR, BUF_TILES_OVERLAP, BUF_PREFIX_SUM, BUF_KEYS_UNSORTED, BUF_VALS_UNSORTED,
- BUF_KEYS_SORTED, BUF_VALS_SORTED, BUF_TILE_BOUNDARY) = range(9)
+ BUF_KEYS_SORTED, BUF_VALS_SORTED, BUF_TILE_BOUNDARY, BUF_DEPTH_ORDER, BUF_EMIT_OFFSETS) = range(11)
 ALL_ROWS = 0xFFFFFFFF
 
 EXPORTED_SYMBOLS = [  # every symbol include/gs_b200.h declares
     "gsb_abi_version", "gsb_device_count", "gsb_create", "gsb_destroy", "gsb_last_error",
     "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers", "gsb_set_tile_cull",
     "gsb_reserve_instances", "gsb_render", "gsb_render_async", "gsb_get_stats", "gsb_debug_size",
-    "gsb_debug_download", "gsb_sort_pairs", "gsb_sort_pairs32",
+    "gsb_debug_download", "gsb_sort_pairs", "gsb_sort_pairs32", "gsb_set_graph", "gsb_host_alloc", "gsb_host_free",
 ]
 HOST_EXPORTED_SYMBOLS = [  # host/gs_b200_host.h
     "gsh_last_error", "gsh_initialize", "gsh_draw", "gsh_pan_translation", "gsh_movement", "gsh_cleanup",
@@ -99,6 +99,10 @@ lib.gsb_set_mode.argtypes = [_vp, C.c_int]
 lib.gsb_set_debug.argtypes = [_vp, C.c_int]
 lib.gsb_set_timers.argtypes = [_vp, C.c_int]
 lib.gsb_set_tile_cull.argtypes = [_vp, C.c_int]
+lib.gsb_set_graph.argtypes = [_vp, C.c_int]
+lib.gsb_host_alloc.argtypes = [C.POINTER(_vp), C.c_size_t]
+lib.gsb_host_free.argtypes = [_vp]
+lib.gsb_host_free.restype = None
 lib.gsb_reserve_instances.argtypes = [_vp, C.c_uint64]
 lib.gsb_render.argtypes = [_vp, C.POINTER(Uniforms), C.c_uint32, C.c_uint32, _vp, C.c_size_t, C.c_int, C.c_int, _vp]
 lib.gsb_render_async.argtypes = [_vp, C.POINTER(Uniforms), C.c_uint32, C.c_uint32, _vp, C.c_size_t, C.c_int, _vp]
@@ -287,6 +291,9 @@ class Context:
     def set_timers(self, on=True):
         self._ck(lib.gsb_set_timers(self.h, int(on)))
 
+    def set_graph(self, on=True):
+        self._ck(lib.gsb_set_graph(self.h, int(on)))
+
     def reserve(self, capacity):
         self._ck(lib.gsb_reserve_instances(self.h, capacity))
 
@@ -321,7 +328,8 @@ class Context:
         nbytes = lib.gsb_debug_size(self.h, which)
         dt = {BUF_COV3D: np.float32, BUF_ATTR: ATTR_DTYPE, BUF_TILES_OVERLAP: np.uint32, BUF_PREFIX_SUM: np.uint32,
               BUF_KEYS_UNSORTED: np.uint64, BUF_VALS_UNSORTED: np.uint32, BUF_KEYS_SORTED: np.uint64,
-              BUF_VALS_SORTED: np.uint32, BUF_TILE_BOUNDARY: np.uint32}[which]
+              BUF_VALS_SORTED: np.uint32, BUF_TILE_BOUNDARY: np.uint32, BUF_DEPTH_ORDER: np.uint32,
+              BUF_EMIT_OFFSETS: np.uint64}[which]
         out = np.empty(nbytes // np.dtype(dt).itemsize, dt)
         if nbytes or which == BUF_COV3D:
             self._ck(lib.gsb_debug_download(self.h, which, out.ctypes.data, nbytes))

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 1
+#define GSB_ABI_VERSION 2
 
 typedef struct gsb_ctx gsb_ctx;
 
@@ -90,7 +90,12 @@ typedef enum gsb_buffer {
     GSB_BUF_VALS_UNSORTED = 5, /* the payloads (Gaussian indices) that go with KEYS_UNSORTED: M * u32 */
     GSB_BUF_KEYS_SORTED = 6,   /* sortKBufferEven after the 8 passes: M * u64 */
     GSB_BUF_VALS_SORTED = 7,   /* sortVBufferEven after the 8 passes: M * u32 (Gaussian indices) */
-    GSB_BUF_TILE_BOUNDARY = 8  /* tileBoundaryBuffer: T * 2 u32                   (Renderer.cpp:321) */
+    GSB_BUF_TILE_BOUNDARY = 8, /* tileBoundaryBuffer: T * 2 u32                   (Renderer.cpp:321) */
+    /* No reference counterpart: the two device results the two-level sort adds, exposed so the
+     * device scan and the Gaussian-level sort are pinned directly and not only through the key placement. */
+    GSB_BUF_DEPTH_ORDER = 9,   /* N_v * u32: Gaussian indices of the cull survivors in (depth bits, index) order */
+    GSB_BUF_EMIT_OFFSETS = 10  /* N_v * u64: k_emit's exclusive scan of the tile counts in that order = the slot of each
+                                  survivor's first instance (prefix_sum.comp's job, in depth order) */
 } gsb_buffer;
 
 /* The reference's six timestamp pairs (src/Renderer.cpp:484-699) + its "instances" text metric
@@ -143,6 +148,14 @@ int gsb_set_debug(gsb_ctx *ctx, int debug);
 int gsb_set_tile_cull(gsb_ctx *ctx, int enabled);
 /* per-stage cudaEvent timers (the QueryManager analogue, Renderer.cpp:85-100). Default on. */
 int gsb_set_timers(gsb_ctx *ctx, int enabled);
+/* Replay the camera-independent middle of the frame (both sorts + key emission) from a captured CUDA graph instead of
+ * ~10 separate launches -- the analogue of the reference's pre-recorded renderCommandBuffer (Renderer.cpp:532-717).
+ * Default on; only used while timers and debug are off (both need per-kernel host calls). */
+int gsb_set_graph(gsb_ctx *ctx, int enabled);
+/* Page-locked host memory for frames / vertex data handed to gsb_render / gsb_scene_upload: copies to and from it are
+ * asynchronous DMA (the reference's host-visible staging buffers, Buffer::staging, src/vulkan/Buffer.cpp). */
+int gsb_host_alloc(void **out, size_t bytes);
+void gsb_host_free(void *p);
 /* Pre-size the (tile,depth) instance arena (the reference's sortBufferSizeMultiplier,
  * Renderer.cpp:541-563, grows N*k on overflow; this does the same between frames). */
 int gsb_reserve_instances(gsb_ctx *ctx, uint64_t capacity);

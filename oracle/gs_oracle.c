@@ -39,6 +39,50 @@ int gso_num_threads(void) {
 #endif
 }
 
+void gso_set_num_threads(int n) { /* torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core it may use */
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* The SURVEY 8d workload generator, restated here so bench.py's reference arm builds the same scene without loading
+ * any product library (counter-based splitmix64; record i depends only on (seed, i); tests/test_oracle.py checks it
+ * bit for bit against the product's gsh_synth_records).  Record = the 62 PLY floats of src/GSScene.cpp:17-24. */
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static double synth_bits_uniform(uint64_t base, uint32_t c) {
+    return (double)(splitmix64(base + (uint64_t)c * 0x632BE59BD9B4E019ull) >> 11) * (1.0 / 9007199254740992.0);
+}
+static double synth_normal(uint64_t base, uint32_t c) { /* Box-Muller on counters 16 + 2c, 17 + 2c */
+    const double u1 = ((double)(splitmix64(base + (uint64_t)(16 + 2 * c) * 0x632BE59BD9B4E019ull) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    const double u2 = synth_bits_uniform(base, 17 + 2 * c);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925 * u2);
+}
+void gso_synth_records(uint64_t seed, uint64_t first, uint64_t n, const gso_synth_params *p, float *records) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 4096)
+#endif
+    for (int64_t kk = 0; kk < (int64_t)n; kk++) {
+        const uint64_t i = first + (uint64_t)kk;
+        const uint64_t base = splitmix64(seed) ^ (i * 128ull);
+        float *r = records + (size_t)kk * GSO_RECORD_FLOATS;
+        for (int a = 0; a < 3; a++) r[a] = (float)(p->center[a] + p->half_extent[a] * (2.0 * synth_bits_uniform(base, (uint32_t)a) - 1.0));
+        r[3] = r[4] = r[5] = 0.0f;
+        for (int a = 0; a < 3; a++) r[6 + a] = (float)(p->sh_dc_range * (2.0 * synth_bits_uniform(base, (uint32_t)(3 + a)) - 1.0));
+        for (int a = 0; a < 45; a++) r[9 + a] = (float)(p->sh_rest_sigma * synth_normal(base, (uint32_t)(4 + a)));
+        r[54] = (float)(p->opacity_min + (p->opacity_max - p->opacity_min) * synth_bits_uniform(base, 6));
+        for (int a = 0; a < 3; a++)
+            r[55 + a] = (float)(p->log_scale_min + (p->log_scale_max - p->log_scale_min) * synth_bits_uniform(base, (uint32_t)(7 + a)));
+        for (int a = 0; a < 4; a++) r[58 + a] = (float)synth_normal(base, (uint32_t)a);
+    }
+}
+
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -513,6 +557,30 @@ void gso_preprocess(const float *vtx, const float *cov, uint64_t n, const gso_un
 
 /* A4. prefix_sum.comp (Hillis-Steele, log2 N + 1 steps) computes exactly an inclusive scan. */
 uint64_t gso_scan_inclusive(const uint32_t *tiles, uint64_t n, uint32_t *scan) {
+#ifdef _OPENMP
+    const int nt = omp_get_max_threads();
+    if (n >= (1u << 16) && nt > 1) { /* two-level scan: per-thread block sums, then offsets (uint32 wraparound kept) */
+        uint32_t *part = (uint32_t *)calloc((size_t)nt + 1, 4);
+#pragma omp parallel num_threads(nt)
+        {
+            const int t = omp_get_thread_num();
+            const uint64_t b = n * (uint64_t)t / (uint64_t)nt, e = n * (uint64_t)(t + 1) / (uint64_t)nt;
+            uint32_t s = 0;
+            for (uint64_t i = b; i < e; i++) s += tiles[i];
+            part[t + 1] = s;
+#pragma omp barrier
+#pragma omp single
+            for (int k = 0; k < nt; k++) part[k + 1] += part[k];
+            s = part[t];
+            for (uint64_t i = b; i < e; i++) {
+                s += tiles[i];
+                scan[i] = s;
+            }
+        }
+        free(part);
+        return scan[n - 1];
+    }
+#endif
     uint32_t s = 0;
     for (uint64_t i = 0; i < n; i++) {
         s += tiles[i]; /* uint32 wraparound like the shader */
@@ -524,7 +592,11 @@ uint64_t gso_scan_inclusive(const uint32_t *tiles, uint64_t n, uint32_t *scan) {
 /* A5. preprocess_sort.comp:31-60 */
 void gso_emit_keys(const gso_attr *attr, const uint32_t *scan, uint64_t n, uint32_t tileX,
                    uint64_t *keys, uint32_t *vals) {
-    for (uint64_t i = 0; i < n; i++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 4096) /* every Gaussian writes its own [scan[i-1], scan[i]) slots */
+#endif
+    for (int64_t ii = 0; ii < (int64_t)n; ii++) {
+        const uint64_t i = (uint64_t)ii;
         const gso_attr *a = &attr[i];
         if (a->color_radii[3] == 0.0f) continue;  /* :37-39 */
         uint32_t ind = i == 0 ? 0 : scan[i - 1]; /* :43 */
@@ -552,20 +624,47 @@ void gso_sort(uint64_t *keys, uint32_t *vals, uint64_t m) {
     uint32_t *v2 = (uint32_t *)malloc((size_t)m * 4);
     uint64_t *ks = keys, *kd = k2;
     uint32_t *vs = vals, *vd = v2;
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+    if (m < (1u << 16)) nt = 1;
+#endif
+    /* hist[t][b]: digit counts of thread t's contiguous chunk.  Offsets are assigned digit-major, thread-minor, so
+     * chunk order (= input order) is kept inside every digit: the same stable counting sort as the serial loop, and
+     * as hist.comp + sort.comp (per-workgroup histograms, digit-major / workgroup-minor offsets, sort.comp:112). */
+    uint64_t *hist = (uint64_t *)malloc((size_t)nt * 256 * 8);
     for (int pass = 0; pass < 8; pass++) { /* Renderer.cpp:598 */
         const int shift = 8 * pass;
-        uint64_t hist[256] = {0};
-        for (uint64_t i = 0; i < m; i++) hist[(ks[i] >> shift) & 255]++;
-        uint64_t sum = 0;
-        for (int b = 0; b < 256; b++) {
-            uint64_t c = hist[b];
-            hist[b] = sum;
-            sum += c;
-        }
-        for (uint64_t i = 0; i < m; i++) {
-            uint64_t p = hist[(ks[i] >> shift) & 255]++;
-            kd[p] = ks[i];
-            vd[p] = vs[i];
+        memset(hist, 0, (size_t)nt * 256 * 8);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nt)
+#endif
+        {
+            int t = 0;
+#ifdef _OPENMP
+            t = omp_get_thread_num();
+#endif
+            const uint64_t b0 = m * (uint64_t)t / (uint64_t)nt, e0 = m * (uint64_t)(t + 1) / (uint64_t)nt;
+            uint64_t *h = hist + (size_t)t * 256;
+            for (uint64_t i = b0; i < e0; i++) h[(ks[i] >> shift) & 255]++;
+#ifdef _OPENMP
+#pragma omp barrier
+#pragma omp single
+#endif
+            {
+                uint64_t sum = 0;
+                for (int b = 0; b < 256; b++)
+                    for (int k = 0; k < nt; k++) {
+                        uint64_t c = hist[(size_t)k * 256 + b];
+                        hist[(size_t)k * 256 + b] = sum;
+                        sum += c;
+                    }
+            }
+            for (uint64_t i = b0; i < e0; i++) {
+                uint64_t p = h[(ks[i] >> shift) & 255]++;
+                kd[p] = ks[i];
+                vd[p] = vs[i];
+            }
         }
         uint64_t *tk = ks;
         ks = kd;
@@ -575,6 +674,7 @@ void gso_sort(uint64_t *keys, uint32_t *vals, uint64_t m) {
         vd = tv;
     }
     /* 8 passes: result is back in the caller's ("Even") buffers, Renderer.cpp:641 */
+    free(hist);
     free(k2);
     free(v2);
 }
@@ -582,7 +682,11 @@ void gso_sort(uint64_t *keys, uint32_t *vals, uint64_t m) {
 /* A7. tile_boundary.comp:22-50 */
 void gso_tile_ranges(const uint64_t *keys, uint64_t m, uint32_t num_tiles, uint32_t *ranges) {
     memset(ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t)); /* Renderer.cpp:633 */
-    for (uint64_t i = 0; i < m; i++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) /* one invocation per key, like the shader; every write has a single writer */
+#endif
+    for (int64_t ii = 0; ii < (int64_t)m; ii++) {
+        const uint64_t i = (uint64_t)ii;
         uint32_t key = (uint32_t)(keys[i] >> 32);
         if (i == 0) {
             ranges[key * 2] = (uint32_t)i;
@@ -628,7 +732,6 @@ void gso_blend(const gso_attr *attr, const uint32_t *vals, const uint32_t *range
                     if (power > 0.0f) continue; /* :68-70 */
                     float e;
                     if (exp_mode == 1) {
-                        if (power < -5.55f) continue; /* alpha <= exp(-5.55) < 1/255 since opacity <= 1 */
                         e = gso_exp_shared(power);
                     } else {
                         e = expf(power);

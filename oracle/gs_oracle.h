@@ -53,10 +53,16 @@ typedef struct gso_attr {
  *   0 = libm expf (default; the plain restatement of GLSL exp, render.comp:77)
  *   1 = "shared-definition" exp: a fixed sequence of correctly-rounded IEEE ops
  *       (Cody-Waite reduction + degree-5 Horner with fmaf) that the CUDA kernel
- *       reproduces bit for bit, plus the conservative power < -5.55 skip the
- *       kernel applies (valid because opacity = sigmoid(.) <= 1, GSScene.cpp:44).
+ *       reproduces bit for bit (the kernel's per-Gaussian early skip only drops pairs
+ *       whose alpha is < 1/255 under this same exp, so it is not part of the definition).
  *       GLSL leaves exp precision implementation-defined, so both are valid
  *       readings of the reference; tests check 0-vs-1 agree to 1e-4. */
+typedef struct gso_synth_params { /* same fields as the product's gsh_synth_params (host/gs_b200_host.h) */
+    float center[3], half_extent[3];
+    float log_scale_min, log_scale_max, opacity_min, opacity_max, sh_dc_range, sh_rest_sigma;
+} gso_synth_params;
+void gso_synth_records(uint64_t seed, uint64_t first, uint64_t n, const gso_synth_params *p, float *records);
+void gso_set_num_threads(int n);
 void gso_set_exp_mode(int mode);
 int gso_get_exp_mode(void);
 float gso_exp_shared(float x);

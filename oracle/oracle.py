@@ -74,6 +74,19 @@ lib.gso_num_threads.restype = C.c_int
 lib.gso_preprocess.argtypes = [_vp, _vp, C.c_uint64, C.POINTER(Uniforms), C.c_uint32, C.c_uint32, _vp, _vp]
 lib.gso_preprocess.restype = None
 
+lib.gso_set_num_threads.argtypes = [C.c_int]
+lib.gso_set_num_threads.restype = None
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("center", C.c_float * 3), ("half_extent", C.c_float * 3), ("log_scale_min", C.c_float),
+                ("log_scale_max", C.c_float), ("opacity_min", C.c_float), ("opacity_max", C.c_float),
+                ("sh_dc_range", C.c_float), ("sh_rest_sigma", C.c_float)]
+
+
+lib.gso_synth_records.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(SynthParams), _vp]
+lib.gso_synth_records.restype = None
+
 STAGES = ["preprocess", "prefix_sum", "preprocess_sort", "sort", "tile_boundary", "render"]
 ALL_ROWS = 0xFFFFFFFF
 
@@ -92,6 +105,29 @@ def exp_shared(x: float) -> float:
 
 def num_threads() -> int:
     return lib.gso_num_threads()
+
+
+def set_num_threads(n: int):
+    lib.gso_set_num_threads(int(n))
+
+
+def synth_params(center=(0, 0, 0), half_extent=(3, 3, 3), log_scale_min=None, log_scale_max=None, opacity_min=-2.0,
+                 opacity_max=4.0, sh_dc_range=1.0, sh_rest_sigma=0.1) -> SynthParams:
+    """Defaults = BASELINE config 1 (the product's gsh_synth_default_params)."""
+    p = SynthParams()
+    p.center[:] = list(center)
+    p.half_extent[:] = list(half_extent)
+    p.log_scale_min = np.float32(np.log(np.float32(0.01))) if log_scale_min is None else log_scale_min
+    p.log_scale_max = np.float32(np.log(np.float32(0.15))) if log_scale_max is None else log_scale_max
+    p.opacity_min, p.opacity_max, p.sh_dc_range, p.sh_rest_sigma = opacity_min, opacity_max, sh_dc_range, sh_rest_sigma
+    return p
+
+
+def synth_records(seed: int, n: int, params: SynthParams | None = None, first: int = 0) -> np.ndarray:
+    params = params or synth_params()
+    out = np.empty((n, 62), np.float32)
+    lib.gso_synth_records(seed, first, n, C.byref(params), out.ctypes.data)
+    return out
 
 
 def load_records(records) -> np.ndarray:
@@ -162,8 +198,9 @@ def uniforms_bytes(u) -> bytes:
     return bytes(memoryview(u))[:160] if not isinstance(u, Uniforms) else bytes(u)
 
 
-def render_frame(vertices, cov, u, rows=None) -> dict:
-    """Runs the whole oracle frame; returns every intermediate as numpy arrays."""
+def render_frame(vertices, cov, u, rows=None, light=False) -> dict:
+    """Runs the whole oracle frame; returns every intermediate as numpy arrays (light=True: counts and stage times only,
+    for timing)."""
     v = _f32(vertices).reshape(-1, 60)
     cv = _f32(cov).reshape(-1, 6)
     ou = Uniforms.from_buffer_copy(bytes(u))  # accept the product's ctypes struct too (same 160-B layout)
@@ -175,6 +212,8 @@ def render_frame(vertices, cov, u, rows=None) -> dict:
         raise MemoryError("oracle frame allocation failed")
     try:
         n, m, T = f.n, f.m, f.tiles_x * f.tiles_y
+        if light:
+            return {"n": n, "m": m, "tiles_x": f.tiles_x, "tiles_y": f.tiles_y, "t_stage": dict(zip(STAGES, list(f.t_stage)))}
 
         def arr(ptr, dtype, count):
             if count == 0:

@@ -44,8 +44,14 @@ def test_frame_intermediates_and_image_exact(gs, oracle, ctx, cam):
         attr = ctx.download(gs.BUF_ATTR)
         for field in ["conic_opacity", "color_radii", "aabb", "uv", "depth", "magic"]:
             assert np.array_equal(attr[field], ref["attr"][field]), field
-        # P1: scan (index order; derived on the host from the device tile counts -- the device scan runs in depth order)
+        # P1: scan.  BUF_PREFIX_SUM is the reference's layout (index order), derived on the host from the device tile
+        # counts; the scan the DEVICE runs is over the depth-sorted survivors inside k_emit and is pinned directly:
         assert np.array_equal(ctx.download(gs.BUF_PREFIX_SUM), ref["scan"])
+        vis = np.nonzero(ref["tiles"] > 0)[0]
+        dorder = vis[np.argsort(ref["attr"]["depth"][vis].view(np.uint32), kind="stable")]  # (depth bits, index) order
+        assert np.array_equal(ctx.download(gs.BUF_DEPTH_ORDER), dorder.astype(np.uint32))   # the Gaussian-level sort
+        excl = np.concatenate([[0], np.cumsum(ref["tiles"][dorder].astype(np.uint64))[:-1]]) if dorder.size else np.empty(0, np.uint64)
+        assert np.array_equal(ctx.download(gs.BUF_EMIT_OFFSETS), excl.astype(np.uint64))    # the device scan
         # P2 + the reference's radix passes 0-3: the device emits the instances in (depth, Gaussian) order, x outer /
         # y inner inside a Gaussian == preprocess_sort.comp's output stably sorted by its low 32 key bits
         order = np.argsort(ref["keys_unsorted"] & np.uint64(0xFFFFFFFF), kind="stable")
@@ -208,3 +214,116 @@ def test_tile_cull_keeps_the_image_bit_exact(gs, oracle, ctx, cam):
     finally:
         ctx.set_tile_cull(False)
         ctx.set_debug(False)
+
+
+def test_device_scan_with_tile_cull(gs, oracle, ctx):
+    """With the exact instance cull on, k_emit scans the CULLED per-Gaussian counts: its offsets must partition the
+    emitted list exactly (offset[j+1] - offset[j] instances of Gaussian depth_order[j], contiguous, in that order)."""
+    _, vtx, u = scenes.c1()
+    ctx.set_debug(True)
+    ctx.set_tile_cull(True)
+    try:
+        ctx.upload(vtx)
+        ctx.render(u, gs.FORMAT_RGBA32F)
+        m = ctx.stats().num_instances
+        order, offs = ctx.download(gs.BUF_DEPTH_ORDER), ctx.download(gs.BUF_EMIT_OFFSETS)
+        vals = ctx.download(gs.BUF_VALS_UNSORTED)
+        assert offs[0] == 0 and np.all(np.diff(offs.astype(np.int64)) >= 0) and offs[-1] <= m
+        counts = np.diff(np.concatenate([offs, [m]]).astype(np.int64))
+        assert np.array_equal(np.repeat(order, counts), vals)
+    finally:
+        ctx.set_tile_cull(False)
+        ctx.set_debug(False)
+
+
+def test_graph_replay_equals_direct_launches(gs, ctx):
+    """gsb_set_graph: the captured middle of the frame (both sorts + emission) replays bit-identically, across cameras,
+    frame sizes and a mid-sequence arena regrow (which invalidates the captured pointers)."""
+    _, vtx, _ = scenes.c1()
+    c = gs.Context(0)
+    try:
+        c.upload(vtx)
+        c.set_timers(False)
+        frames = {}
+        for graph in (False, True):
+            c.set_graph(graph)
+            for rep in range(2):
+                for cam in ("c1", "inside", "odd_size", "wide", "tiny", "c1"):
+                    img = c.render(scenes.camera(cam), gs.FORMAT_RGBA32F)
+                    assert np.array_equal(frames.setdefault(cam, img), img), (graph, cam)
+        c.set_timers(True)
+        assert np.array_equal(c.render(scenes.camera("c1"), gs.FORMAT_RGBA32F), frames["c1"])
+        assert c.stats().frame_ms > 0
+    finally:
+        c.close()
+
+
+def test_async_overflow_is_sticky(gs, ctx):
+    """an overflow in ANY gsb_render_async frame must be reported by the next gsb_get_stats, even if later
+    frames fit (each frame rewrites the per-frame flag)."""
+    import torch
+    _, vtx, _ = scenes.c1(n=3000)
+    c = gs.Context(0)
+    try:
+        c.upload(vtx)  # arena = 3000 entries
+        big, small = scenes.camera("c1"), scenes.camera("away")  # "away": everything culled, M = 0
+        out = torch.zeros((480, 640, 4), dtype=torch.float32, device="cuda:0")
+        c.render_into(big, out.data_ptr(), gs.FORMAT_RGBA32F, sync=False)    # overflows (M > 3000)
+        small_out = torch.zeros((240, 320, 4), dtype=torch.float32, device="cuda:0")
+        c.render_into(small, small_out.data_ptr(), gs.FORMAT_RGBA32F, sync=False)  # fits
+        with pytest.raises(gs.GsbError) as e:
+            c.stats()
+        assert e.value.code == gs.ERR_OVERFLOW
+        c.render_into(small, small_out.data_ptr(), gs.FORMAT_RGBA32F, sync=False)
+        assert c.stats().num_instances == 0  # reported once, then cleared
+    finally:
+        c.close()
+
+
+def test_opacity_above_one_matches_the_shader(gs, oracle):
+    """ADVICE r1: gsb_scene_upload takes raw GSScene::Vertex arrays; an opacity > 1 lowers the alpha >= 1/255 cut below
+    -5.55 and the kernel must keep those pairs exactly like render.comp:77-80 (min(0.99, opacity * exp(power)))."""
+    _, vtx, u = scenes.c1(n=2000)
+    vtx = vtx.copy()
+    vtx[::3, 7] = 40.0   # scale_opacity.w
+    vtx[1::7, 7] = 3.0
+    c = gs.Context(0)
+    try:
+        c.upload(vtx)
+        for cull in (False, True):
+            c.set_tile_cull(cull)
+            img = c.render(u, gs.FORMAT_RGBA32F)
+            ref = oracle_frame(oracle, vtx, u, 1)
+            assert np.array_equal(img, ref["rgba"]), cull
+            assert np.abs(img - oracle_frame(oracle, vtx, u, 0)["rgba"]).max() <= TOL
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("fmt_name", ["FORMAT_RGBA32F", "FORMAT_BGRA8"])
+def test_host_output_bands_equal_device_output(gs, ctx, fmt_name):
+    """gsb_render to HOST memory blends in row bands and copies each band while the next ones blend; pageable, pinned
+    and pitched destinations must all equal the single-kernel device-output frame."""
+    import ctypes as C
+    import torch
+    _, vtx, _ = scenes.c1()
+    fmt = getattr(gs, fmt_name)
+    ctx.upload(vtx)
+    for cam in ("c1", "odd_size", "tiny", "wide"):
+        u = scenes.camera(cam)
+        bpp = 16 if fmt == gs.FORMAT_RGBA32F else 4
+        dt = torch.float32 if fmt == gs.FORMAT_RGBA32F else torch.uint8
+        dev = torch.zeros((u.height, u.width, 4), dtype=dt, device="cuda:0")
+        ctx.render_into(u, dev.data_ptr(), fmt, sync=True)
+        ref = dev.cpu().numpy()
+        assert np.array_equal(ctx.render(u, fmt), ref)                       # pageable numpy destination
+        p = C.c_void_p()
+        pitch = u.width * bpp + 64                                           # pinned + padded rows
+        assert gs.lib.gsb_host_alloc(C.byref(p), pitch * u.height) == 0
+        try:
+            ctx._ck(gs.lib.gsb_render(ctx.h, C.byref(u), 0, gs.ALL_ROWS, p, pitch, gs.MEM_HOST, fmt, None))
+            raw = np.frombuffer((C.c_char * (pitch * u.height)).from_address(p.value), np.uint8).reshape(u.height, pitch)
+            got = raw[:, :u.width * bpp].copy().view(ref.dtype).reshape(ref.shape)
+            assert np.array_equal(got, ref)
+        finally:
+            gs.lib.gsb_host_free(p)

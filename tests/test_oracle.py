@@ -213,3 +213,37 @@ def test_pack_unorm8(oracle):
     assert rgba.reshape(2, 4).tolist() == [[0, 0, 128, 255], [255, 0, 254, 0]]   # 127.5 -> 128 (RNE), NaN -> 0
     bgra = oracle.pack_unorm8(x, bgra=True)
     assert bgra.reshape(2, 4).tolist() == [[128, 0, 0, 255], [254, 0, 255, 0]]
+
+
+def test_oracle_scene_generator_equals_the_products(gs, oracle):
+    """bench.py's reference arm builds its scene with the oracle's restatement of the SURVEY 8d generator so that it
+    loads no product library; both generators (and both activations) must agree bit for bit."""
+    import math
+    assert np.array_equal(gs.synth_records(42, 70_000), oracle.synth_records(42, 70_000))
+    kw = dict(center=(0, 0, 0), half_extent=(10.0, 4.0, 10.0), log_scale_min=math.log(0.003), log_scale_max=math.log(0.05))
+    a = gs.synth_records(3, 100_000, gs.synth_params(**kw), first=5_000_000)
+    b = oracle.synth_records(3, 100_000, oracle.synth_params(**kw), first=5_000_000)
+    assert np.array_equal(a, b)
+    assert np.array_equal(gs.activate_records(a), oracle.load_records(b))
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_parallel_sort_scan_are_the_serial_ones(oracle, threads):
+    """gso_sort / gso_scan_inclusive run OpenMP-parallel above 64 Ki elements: still the stable LSD sort and the exact
+    inclusive scan (uint32 wraparound) of the reference."""
+    rng = np.random.default_rng(5)
+    m = 300_007
+    keys = (rng.integers(0, 700, m).astype(np.uint64) << np.uint64(32)) | rng.integers(0, 50, m).astype(np.uint64) * np.uint64(0x01010101)
+    vals = np.arange(m, dtype=np.uint32)
+    oracle.set_num_threads(threads)
+    try:
+        k, v = oracle.sort_pairs(keys, vals)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k, keys[order]) and np.array_equal(v, vals[order])
+        tiles = rng.integers(0, 2**31, 200_000).astype(np.uint32)  # sums wrap around uint32
+        scan = np.empty_like(tiles)
+        oracle.lib.gso_scan_inclusive.restype = oracle.C.c_uint64
+        oracle.lib.gso_scan_inclusive(tiles.ctypes.data_as(oracle.C.c_void_p), oracle.C.c_uint64(tiles.size), scan.ctypes.data_as(oracle.C.c_void_p))
+        assert np.array_equal(scan, np.cumsum(tiles.astype(np.uint64)).astype(np.uint32))
+    finally:
+        oracle.set_num_threads(max(1, len(__import__("os").sched_getaffinity(0))))
