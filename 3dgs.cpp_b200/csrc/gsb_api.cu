@@ -4,6 +4,7 @@
 // pipeline barriers, kernel arguments instead of descriptor sets, and no mid-frame host sync.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -78,12 +79,12 @@ struct gsb_ctx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_sort[9] = {};  // instance sort: after hist, after each pass
     cudaEvent_t ev_done = nullptr;
-    cudaEvent_t ev_band[8] = {};  // host-output frames: blend band b finished (its D2H copy may start)
-    cudaStream_t copy_stream = nullptr;
     bool frame_pending = false;
     bool have_frame = false;
     bool frame_debug = false;   // the last frame ran with gsb_set_debug on (its debug buffers and sorted keys exist)
     bool frame_timers = false;  // the last frame recorded the stage events (gsb_get_stats may read them)
+    bool host_direct = true;    // gsb_render to page-locked host memory: blend straight into it (GSB_HOST_DIRECT=0: always stage)
+    int blend_variant = 2;      // GSB_BLEND_VARIANT=1 selects the round-1 one-pixel-per-thread kernel (A/B only)
     bool use_graph = true;      // replay the sorts + key emission from a captured CUDA graph when timers and debug are off
     uint64_t alloc_gen = 0;     // bumped by every (re)allocation a captured graph could point into
     uint64_t graph_clock = 0;
@@ -454,6 +455,9 @@ int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, v
     bp.row_pitch_bytes = pitch;
     bp.format = fmt;
     bp.mode = ctx->mode;
+    bp.variant = ctx->blend_variant;
+    bp.stats = (ctx->timers || ctx->debug) ? 1 : 0;
+    bp.one = 1.0f;
     bp.ctl = ctx->ctl;
     CK(launch_blend(bp, stream));
     return GSB_OK;
@@ -556,11 +560,10 @@ int gsb_create(int device, gsb_ctx** out) {
         return GSB_ERR_NO_DEVICE;
     }
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* v = getenv("GSB_BLEND_VARIANT")) ctx->blend_variant = atoi(v) == 1 ? 1 : 2;
+    if (const char* v = getenv("GSB_HOST_DIRECT")) ctx->host_direct = atoi(v) != 0;
     if ((e = sort_prepare()) != cudaSuccess) return bail("sort_prepare", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-    for (auto& ev : ctx->ev_band)
-        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = dev_alloc(&ctx->ctl, 1)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMemset(ctx->ctl, 0, sizeof(Control))) != cudaSuccess) return bail("cudaMemset", e);  // epoch and overflow_sticky start at 0
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return bail("cudaDeviceSynchronize", e);
@@ -582,9 +585,6 @@ void gsb_destroy(gsb_ctx* ctx) {
     cudaDeviceSynchronize();
     drop_graphs(ctx);
     dev_free(ctx->dbg_offsets);
-    for (auto& ev : ctx->ev_band)
-        if (ev) cudaEventDestroy(ev);
-    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     dev_free(ctx->pos_op);
     dev_free(ctx->cov_a);
     dev_free(ctx->cov_b);
@@ -784,43 +784,37 @@ int gsb_render(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
     const uint32_t rows = std::min(H, re * GSB_TILE) - rb * GSB_TILE;
     const size_t tight = (size_t)ubo->width * bytes_per_pixel(fmt);
 
+    // Host output.  If `out` is page-locked (gsb_host_alloc / cudaHostAlloc / cudaHostRegister) the blend stores the frame
+    // straight into it over PCIe: k_blend2 writes whole 64-B tile rows, the stores are posted and the kernel is issue-bound,
+    // so the 17.9 MB of a 3200x1400 BGRA8 frame leave the GPU while the blend is still running and no copy is left at the
+    // end (the reference likewise stores into a host-visible swapchain image, render.comp:98).  Pageable memory goes
+    // through a device staging frame and one cudaMemcpy2D.
     void* dev_out = out;
     size_t dev_pitch = pitch;
+    bool staged = false;
     if (out_mem == GSB_MEM_HOST) {
-        const size_t need = tight * rows;
-        if (need > ctx->fb_bytes) {
-            if (ctx->fb) cudaFree(ctx->fb);
-            ctx->fb = nullptr;
-            ctx->fb_bytes = 0;
-            CK(cudaMalloc(&ctx->fb, need));
-            ctx->fb_bytes = need;
-        }
-        dev_out = ctx->fb;
-        dev_pitch = tight;
-    }
-    // Host output: the blend runs in up to 8 row bands and every finished band is copied device -> host on a second stream
-    // while the next bands are still blending, so only the last band's copy is exposed (17.9 MB BGRA8 at 3200x1400 is
-    // ~0.33 ms of PCIe time, the blend ~0.65 ms).  Pinned `out` (gsb_host_alloc) makes the copies truly asynchronous.
-    const uint32_t band_rows = re - rb;
-    const uint32_t nb = out_mem == GSB_MEM_HOST ? std::min<uint32_t>(8u, band_rows) : 1u;
-    for (int attempt = 0;; attempt++) {
-        FramePlan fp{};
-        rc = enqueue_front(ctx, ubo, rb, re, s, &fp);
-        if (rc != GSB_OK) return rc;
-        for (uint32_t b = 0; b < nb; b++) {
-            const uint32_t b0 = rb + (uint32_t)((uint64_t)band_rows * b / nb), b1 = rb + (uint32_t)((uint64_t)band_rows * (b + 1) / nb);
-            rc = enqueue_blend(ctx, fp, b0, b1, dev_out, dev_pitch, fmt, s);
-            if (rc != GSB_OK) return rc;
-            if (out_mem == GSB_MEM_HOST) {
-                const uint32_t y0 = (b0 - rb) * GSB_TILE, y1 = std::min(H, b1 * GSB_TILE) - rb * GSB_TILE;
-                CK(cudaEventRecord(ctx->ev_band[b], s));
-                CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band[b], 0));
-                CK(cudaMemcpy2DAsync(static_cast<unsigned char*>(out) + (size_t)y0 * pitch, pitch,
-                                     static_cast<unsigned char*>(dev_out) + (size_t)y0 * dev_pitch, dev_pitch, tight, y1 - y0,
-                                     cudaMemcpyDeviceToHost, ctx->copy_stream));
+        cudaPointerAttributes pa{};
+        const bool pinned = ctx->host_direct && cudaPointerGetAttributes(&pa, out) == cudaSuccess &&
+                            pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr;
+        cudaGetLastError();
+        if (pinned) {
+            dev_out = pa.devicePointer;
+        } else {
+            const size_t need = tight * rows;
+            if (need > ctx->fb_bytes) {
+                if (ctx->fb) cudaFree(ctx->fb);
+                ctx->fb = nullptr;
+                ctx->fb_bytes = 0;
+                CK(cudaMalloc(&ctx->fb, need));
+                ctx->fb_bytes = need;
             }
+            dev_out = ctx->fb;
+            dev_pitch = tight;
+            staged = true;
         }
-        rc = enqueue_tail(ctx, fp, s);
+    }
+    for (int attempt = 0;; attempt++) {
+        rc = enqueue_frame(ctx, ubo, rb, re, dev_out, dev_pitch, fmt, s);
         if (rc != GSB_OK) return rc;
         rc = wait_frame(ctx);
         if (rc != GSB_OK) return rc;
@@ -828,13 +822,15 @@ int gsb_render(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
         // arena overflow: grow like the reference's sortBufferSizeMultiplier retry (Renderer.cpp:541-563)
         if (attempt >= 3) return fail(ctx, GSB_ERR_OVERFLOW, "instance arena overflow persists after regrow");
         const uint64_t want = ctx->ctl_host->instances_total + ctx->ctl_host->instances_total / 4 + 4096;
-        if (out_mem == GSB_MEM_HOST) CK(cudaStreamSynchronize(ctx->copy_stream));
         rc = ensure_arena(ctx, want);
         if (rc != GSB_OK) return rc;
         CK(cudaMemsetAsync(&ctx->ctl->overflow_sticky, 0, sizeof(uint32_t), s));  // this overflow is being handled right here
         ctx->regrow_count++;
     }
-    if (out_mem == GSB_MEM_HOST) CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (staged) {
+        CK(cudaMemcpy2DAsync(out, pitch, dev_out, dev_pitch, tight, rows, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     return GSB_OK;
 }
 
@@ -855,6 +851,7 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
     out->num_instances = c->instances_total;
     out->num_instances_aabb = c->candidates_total;
     out->blend_consumed = c->blend_consumed;
+    out->blend_warp_visits = c->blend_walked;
     out->instance_capacity = ctx->capacity;
     out->sort_passes = ctx->last_passes;
     out->sort_depth_passes = ctx->last_depth_passes;

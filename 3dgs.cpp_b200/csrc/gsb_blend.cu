@@ -278,14 +278,332 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
     if (tid == 0 && s_used) atomicAdd(&P.ctl->blend_consumed, (unsigned long long)s_used);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_blend2 -- two pixels per thread, packed fp32 (Blackwell FMUL2 / FADD2 / FFMA2 = PTX *.f32x2).
+//
+// One CTA of 128 threads owns one 16x16 tile; warp w owns the 8x8 pixel block at (8 (w & 1), 8 (w >> 1)) and lane
+// (lx = lane & 7, ly = lane >> 3) owns the two pixels (lx, ly) and (lx, ly + 4) of it.  Every arithmetic step of
+// render.comp:64-88 is issued once for both pixels as one packed instruction; each half of a packed instruction is the
+// same single correctly rounded IEEE operation as its scalar form, so EXACT mode stays bit-identical to the oracle.
+// Measured on B200 (tools/ubench/f32x2.cu): FMUL2 / FADD2 issue at the scalar rate (2x the lanes per issue slot), FFMA2
+// at half of it (same lanes per cycle as FFMA) -- the kernel is issue-bound, so what counts is that the per-record loop
+// drops from 51.5 instructions per 32 pixels to ~66 per 64 pixels.  The comparisons and selects of the shader's
+// `continue` / `break` logic have no packed form and stay per pixel.
+// Staged records are stored pre-broadcast ((ux, ux), (A', A'), ...) so that every packed operand is an aligned register
+// pair straight out of an LDS.128: no MOVs in the loop.  Per-warp survivor lists, per-block conservative culling
+// (8x8 blocks) and the batch pipeline are those of k_blend.
+// ------------------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// EXACT-mode add whose first operand is a packed PRODUCT.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// though both carry .rn (it honours .rn for scalar f32; -fmad=false, volatile asm and a constant 1.0 multiplier do not
+// stop it -- checked in SASS), which would change the rounding of render.comp:66/:87.  Two ways to keep the two roundings:
+//   GSB_BLEND2_ADD == 1: a + b = fma(a, 1.0, b) with the 1.0 coming from a kernel argument (opaque to ptxas), one FFMA2
+//                        with a uniform-register operand;
+//   GSB_BLEND2_ADD == 0: two scalar add.rn.f32 on the halves.
+#ifndef GSB_BLEND2_ADD
+#define GSB_BLEND2_ADD 1
+#endif
+__device__ __forceinline__ u64 add2_of_product(u64 prod, u64 b, u64 one2) {
+#if GSB_BLEND2_ADD
+    return fma2(prod, one2, b);
+#else
+    float p0, p1, b0, b1;
+    upk2(prod, p0, p1);
+    upk2(b, b0, b1);
+    return pk2(__fadd_rn(p0, b0), __fadd_rn(p1, b1));
+#endif
+}
+// two 64-bit register pairs out of one LDS.128
+__device__ __forceinline__ void lds_2x64(uint32_t addr, u64& a, u64& b) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+
+#ifndef GSB_BLEND2_BATCH
+#define GSB_BLEND2_BATCH 256  // records staged per batch (2 per thread)
+#endif
+#ifndef GSB_BLEND2_MIN_BLOCKS
+#define GSB_BLEND2_MIN_BLOCKS 8
+#endif
+#ifndef GSB_BLEND2_CHECK
+#define GSB_BLEND2_CHECK 8
+#endif
+constexpr int B2_THREADS = 128;
+constexpr int B2_BATCH = GSB_BLEND2_BATCH;
+constexpr int B2_WARPS = B2_THREADS / 32;
+
+struct __align__(16) StagedRec2 {  // 80 B: five 16-B slots = five LDS.128 per visited record
+    float4 q0;  // ux ux uy uy
+    float4 q1;  // -A/2 -A/2 -B -B       (exact power-of-two / sign scalings of the conic, as in k_blend)
+    float4 q2;  // -C/2 -C/2 opacity opacity
+    float4 q3;  // r r g g
+    float4 q4;  // b b power_cut bits(index in batch)
+};
+
+__device__ __forceinline__ uint32_t block_mask2(float ux, float uy, float A, float B, float C, float cut, float tile_x0, float tile_y0) {
+    if (!(A > 0.0f) || !(C > 0.0f)) return 0xfu;  // not positive definite / NaN: never cull
+    const float inv_a = __frcp_rn(A), inv_c = __frcp_rn(C);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int w = 0; w < B2_WARPS; w++) {
+        const float x0 = tile_x0 + (float)((w & 1) * 8), y0 = tile_y0 + (float)((w >> 1) * 8);
+        if (rect_may_contribute(ux, uy, A, B, C, inv_a, inv_c, x0, y0, 8.0f, 8.0f, cut)) mask |= 1u << w;
+    }
+    return mask;
+}
+
+// exp for both pixels; same operation sequence as exp_shared without the clamp at -87 (identity on [cut, 0] with
+// cut >= -87, and results for powers outside that range are never selected)
+__device__ __forceinline__ void exp_shared2(u64 x, u64 one2, float& e0, float& e1) {
+    const u64 L2E = pk2(1.44269504088896341f, 1.44269504088896341f), MAGIC = pk2(12582912.0f, 12582912.0f);
+    const u64 t = mul2(x, L2E);
+    const u64 tm = add2_of_product(t, MAGIC, one2);
+    const u64 n = sub2(tm, MAGIC);
+    u64 r = fma2(n, pk2(-0.693359375f, -0.693359375f), x);
+    r = fma2(n, pk2(2.12194440e-4f, 2.12194440e-4f), r);
+    u64 p = fma2(pk2(8.290082216262817e-3f, 8.290082216262817e-3f), r, pk2(4.1899293661117554e-2f, 4.1899293661117554e-2f));
+    p = fma2(p, r, pk2(1.6667647659778595e-1f, 1.6667647659778595e-1f));
+    p = fma2(p, r, pk2(4.9999138712882996e-1f, 4.9999138712882996e-1f));
+    p = fma2(p, r, pk2(9.999997019767761e-1f, 9.999997019767761e-1f));
+    p = fma2(p, r, pk2(1.0f, 1.0f));
+    float p0, p1, m0, m1;
+    upk2(p, p0, p1);
+    upk2(tm, m0, m1);
+    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(m0) << 23));
+    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(m1) << 23));
+}
+
+template <int MODE, bool STATS>
+__global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(const __grid_constant__ BlendParams P) {
+    __shared__ StagedRec2 s_rec[B2_BATCH];
+    __shared__ uint8_t s_mask[B2_BATCH];
+    __shared__ uint16_t s_list[B2_WARPS][B2_BATCH];  // per warp: shared-window addresses of the records it must visit
+    __shared__ uint32_t s_used, s_walked;
+    static_assert(sizeof(StagedRec2) * B2_BATCH < 65536, "u16 list entries hold shared-window addresses");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tx = blockIdx.x % P.tiles_x;
+    const uint32_t ty = P.tile_row_begin + blockIdx.x / P.tiles_x;
+    uint2 range = P.ranges[ty * P.tiles_x + tx];  // render.comp:43-44; stored as (start, ~end), empty = all ones
+    range.y = ~range.y;
+    const uint32_t px = tx * GSB_TILE + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py0 = ty * GSB_TILE + (warp >> 1) * 8 + (lane >> 3), py1 = py0 + 4;
+    const bool in0 = px < P.width && py0 < P.height, in1 = px < P.width && py1 < P.height;  // :37-39
+    const u64 fx2 = pk2((float)px, (float)px), fy2 = pk2((float)py0, (float)py1);
+    const u64 one2 = pk2(P.one, P.one);  // 1.0f the compiler cannot see (add2_of_product)
+    const float tile_x0 = (float)(tx * GSB_TILE), tile_y0 = (float)(ty * GSB_TILE);
+    if (tid == 0) {
+        s_used = 0;
+        s_walked = 0;
+    }
+    __syncthreads();
+
+    float T0 = 1.0f, T1 = 1.0f, ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f, cc0 = 0.f, cc1 = 0.f;  // colour a/b/c of pixel 0/1
+    bool done0 = !in0, done1 = !in1;
+    uint32_t used = 0, walked = 0;
+    const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);
+    const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
+
+    for (uint32_t base = range.x; base < range.y; base += B2_BATCH) {
+        const uint32_t cnt = min((uint32_t)B2_BATCH, range.y - base);
+#pragma unroll
+        for (int j = 0; j < B2_BATCH / B2_THREADS; j++) {
+            const uint32_t li = (uint32_t)(j * B2_THREADS + tid);
+            if (li < cnt) {
+                const uint32_t cid = __ldg(P.vals + base + li);
+                const float4* rec = P.recs + (size_t)cid * 3;
+                const float4 a = __ldg(rec), b = __ldg(rec + 1);
+                const float cb = __ldg(reinterpret_cast<const float*>(rec + 2));
+                const float cut = power_cut(b.y);
+                const float na = -0.5f * a.z, nb = -a.w, nc = -0.5f * b.x;
+                s_rec[li].q0 = make_float4(a.x, a.x, a.y, a.y);
+                s_rec[li].q1 = make_float4(na, na, nb, nb);
+                s_rec[li].q2 = make_float4(nc, nc, b.y, b.y);
+                s_rec[li].q3 = make_float4(b.z, b.z, b.w, b.w);
+                s_rec[li].q4 = make_float4(cb, cb, cut, __uint_as_float(li));
+                s_mask[li] = (uint8_t)block_mask2(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
+            }
+        }
+        __syncthreads();
+        if (!__all_sync(FULL, done0 && done1)) {
+            uint32_t n = 0;
+            for (uint32_t c = 0; c < cnt; c += 32) {  // one ballot per 32 records
+                const bool mine = (c + lane < cnt) && ((s_mask[c + lane] >> warp) & 1u);
+                const unsigned bits = __ballot_sync(FULL, mine);
+                if (mine) s_list[warp][n + __popc(bits & ((1u << lane) - 1u))] = (uint16_t)(rec_sh + (c + lane) * sizeof(StagedRec2));
+                n += __popc(bits);
+            }
+            __syncwarp();
+            const uint32_t base_off = base - range.x;
+            uint32_t k0 = 0;
+            for (; k0 < n; k0 += GSB_BLEND2_CHECK) {
+                if (__all_sync(FULL, done0 && done1)) break;
+                const uint32_t k1 = min(n, k0 + (uint32_t)GSB_BLEND2_CHECK);
+                for (uint32_t k = k0; k < k1; k++) {
+                    const uint32_t addr = lds_u16(list_sh + 2u * k);
+                    u64 ux2, uy2, A2, B2, C2, op2, r2, g2, b2, misc;
+                    lds_2x64(addr, ux2, uy2);
+                    lds_2x64(addr + 16u, A2, B2);
+                    lds_2x64(addr + 32u, C2, op2);
+                    lds_2x64(addr + 48u, r2, g2);
+                    lds_2x64(addr + 64u, b2, misc);
+                    float cut, idxf;
+                    upk2(misc, cut, idxf);
+                    const u64 dx2 = sub2(ux2, fx2), dy2 = sub2(uy2, fy2);  // :64
+                    float pw0, pw1, al0, al1;
+                    u64 alpha2;
+                    if (MODE == GSB_MODE_EXACT) {
+                        // :66 with the pre-scaled conic: ((A' dx) dx + (C' dy) dy) + (B' dx) dy
+                        const u64 s2 = add2_of_product(mul2(mul2(A2, dx2), dx2), mul2(mul2(C2, dy2), dy2), one2);
+                        const u64 pw2 = add2_of_product(mul2(mul2(B2, dx2), dy2), s2, one2);  // s + t3 == t3 + s (commutative, one rounding)
+                        upk2(pw2, pw0, pw1);
+                        float e0, e1;
+                        exp_shared2(pw2, one2, e0, e1);
+                        float o0, o1;
+                        upk2(mul2(op2, pk2(e0, e1)), o0, o1);  // :77
+                        al0 = fminf(0.99f, o0);
+                        al1 = fminf(0.99f, o1);
+                    } else {
+                        const u64 pw2 = fma2(mul2(A2, dx2), dx2, fma2(mul2(C2, dy2), dy2, mul2(mul2(B2, dx2), dy2)));
+                        upk2(pw2, pw0, pw1);
+                        float o0, o1;
+                        upk2(op2, o0, o1);
+                        al0 = fminf(0.99f, o0 * __expf(pw0));
+                        al1 = fminf(0.99f, o1 * __expf(pw1));
+                    }
+                    alpha2 = pk2(al0, al1);
+                    // :68-70 and, below the Gaussian's cut, alpha < 1/255 (:78); a NaN power passes like in the shader
+                    bool ok0 = !done0 && !(pw0 > 0.0f || pw0 < cut) && !(al0 < 1.0f / 255.0f);  // :78-80
+                    bool ok1 = !done1 && !(pw1 > 0.0f || pw1 < cut) && !(al1 < 1.0f / 255.0f);
+                    float tt0, tt1;
+                    const u64 T2 = pk2(T0, T1);
+                    upk2(mul2(T2, sub2(pk2(1.0f, 1.0f), alpha2)), tt0, tt1);  // :82
+                    const bool fin0 = ok0 && tt0 < 0.0001f, fin1 = ok1 && tt1 < 0.0001f;  // :83-85
+                    done0 = done0 || fin0;
+                    done1 = done1 || fin1;
+                    ok0 = ok0 && !fin0;
+                    ok1 = ok1 && !fin1;
+                    if (STATS) {
+                        const uint32_t u = base_off + __float_as_uint(idxf) + 1u;
+                        used = (fin0 || fin1) ? max(used, u) : used;
+                    }
+                    float na0, na1, nb0, nb1, nc0, nc1;
+                    if (MODE == GSB_MODE_EXACT) {
+                        upk2(add2_of_product(mul2(mul2(r2, alpha2), T2), pk2(ca0, ca1), one2), na0, na1);  // :87
+                        upk2(add2_of_product(mul2(mul2(g2, alpha2), T2), pk2(cb0, cb1), one2), nb0, nb1);
+                        upk2(add2_of_product(mul2(mul2(b2, alpha2), T2), pk2(cc0, cc1), one2), nc0, nc1);
+                    } else {
+                        const u64 w2 = mul2(alpha2, T2);
+                        upk2(fma2(r2, w2, pk2(ca0, ca1)), na0, na1);
+                        upk2(fma2(g2, w2, pk2(cb0, cb1)), nb0, nb1);
+                        upk2(fma2(b2, w2, pk2(cc0, cc1)), nc0, nc1);
+                    }
+                    ca0 = ok0 ? na0 : ca0;
+                    cb0 = ok0 ? nb0 : cb0;
+                    cc0 = ok0 ? nc0 : cc0;
+                    T0 = ok0 ? tt0 : T0;  // :88
+                    ca1 = ok1 ? na1 : ca1;
+                    cb1 = ok1 ? nb1 : cb1;
+                    cc1 = ok1 ? nc1 : cc1;
+                    T1 = ok1 ? tt1 : T1;
+                }
+            }
+            if (STATS) {
+                walked += min(k0, n);
+                if (!(done0 && done1)) used = base_off + cnt;  // a live pixel read the whole batch
+            }
+        }
+        if (__syncthreads_and(done0 && done1)) break;
+    }
+
+    if (STATS) {
+        if (in0 || in1) atomicMax(&s_used, used);
+        if (lane == 0 && walked) atomicAdd(&s_walked, walked);
+    }
+    unsigned char* band = static_cast<unsigned char*>(P.out);
+    const uint32_t row0 = py0 - P.tile_row_begin * GSB_TILE;
+    if (P.format == GSB_FORMAT_RGBA32F) {
+        if (in0) reinterpret_cast<float4*>(band + (size_t)row0 * P.row_pitch_bytes)[px] = make_float4(ca0, cb0, cc0, 1.0f);  // :98 vec4(c, 1)
+        if (in1) reinterpret_cast<float4*>(band + (size_t)(row0 + 4) * P.row_pitch_bytes)[px] = make_float4(ca1, cb1, cc1, 1.0f);
+    } else {
+        // 8-bit formats: transpose the tile through shared memory so that every warp store covers whole 64-B tile rows
+        // (also what lets gsb_render write a pinned host frame directly at a good PCIe payload size)
+        __syncthreads();  // everyone is out of the batch loop: s_rec can be reused
+        uint32_t* s_tile = reinterpret_cast<uint32_t*>(&s_rec[0]);  // [16][16]
+        const bool bgra = P.format == GSB_FORMAT_BGRA8;
+        {
+            const uint32_t r0 = unorm8(ca0), g0 = unorm8(cb0), b0 = unorm8(cc0), r1 = unorm8(ca1), g1 = unorm8(cb1), b1 = unorm8(cc1);
+            const uint32_t lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 8 + (lane >> 3);
+            s_tile[ly * 16 + lx] = bgra ? (b0 | (g0 << 8) | (r0 << 16) | 0xff000000u) : (r0 | (g0 << 8) | (b0 << 16) | 0xff000000u);
+            s_tile[(ly + 4) * 16 + lx] = bgra ? (b1 | (g1 << 8) | (r1 << 16) | 0xff000000u) : (r1 | (g1 << 8) | (b1 << 16) | 0xff000000u);
+        }
+        __syncthreads();
+        if (tid < 64) {  // thread -> (row = tid / 4, 4 pixels at x = 4 (tid % 4)): 4 consecutive threads = one 64-B tile row
+            const uint32_t ry = (uint32_t)tid >> 2, rx = ((uint32_t)tid & 3u) * 4u;
+            const uint32_t gy = ty * GSB_TILE + ry, gx = tx * GSB_TILE + rx;
+            if (gy < P.height && gx < P.width) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(band + (size_t)(gy - P.tile_row_begin * GSB_TILE) * P.row_pitch_bytes) + gx;
+                const uint4 v = *reinterpret_cast<const uint4*>(&s_tile[ry * 16 + rx]);
+                if (gx + 3 < P.width && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                    *reinterpret_cast<uint4*>(dst) = v;
+                } else {  // ragged right edge (W not a multiple of 4) or an unaligned pitch
+                    const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+                    for (uint32_t q = 0; q < 4 && gx + q < P.width; q++) dst[q] = e[q];
+                }
+            }
+        }
+    }
+    if (STATS) {
+        __syncthreads();
+        if (tid == 0) {
+            if (s_used) atomicAdd(&P.ctl->blend_consumed, (unsigned long long)s_used);
+            if (s_walked) atomicAdd(&P.ctl->blend_walked, (unsigned long long)s_walked);
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_blend(const BlendParams& p, cudaStream_t s) {
     const uint32_t rows = p.tile_row_end - p.tile_row_begin;
     const uint32_t blocks = rows * p.tiles_x;
     if (blocks == 0) return cudaSuccess;
-    if (p.mode == GSB_MODE_EXACT) k_blend<GSB_MODE_EXACT><<<blocks, BLEND_THREADS, 0, s>>>(p);
-    else k_blend<GSB_MODE_FAST><<<blocks, BLEND_THREADS, 0, s>>>(p);
+    if (p.variant == 1) {  // round-1 kernel (one pixel per thread), kept for A/B: GSB_BLEND_VARIANT=1
+        if (p.mode == GSB_MODE_EXACT) k_blend<GSB_MODE_EXACT><<<blocks, BLEND_THREADS, 0, s>>>(p);
+        else k_blend<GSB_MODE_FAST><<<blocks, BLEND_THREADS, 0, s>>>(p);
+    } else if (p.stats) {
+        if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, true><<<blocks, B2_THREADS, 0, s>>>(p);
+        else k_blend2<GSB_MODE_FAST, true><<<blocks, B2_THREADS, 0, s>>>(p);
+    } else {
+        if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, false><<<blocks, B2_THREADS, 0, s>>>(p);
+        else k_blend2<GSB_MODE_FAST, false><<<blocks, B2_THREADS, 0, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

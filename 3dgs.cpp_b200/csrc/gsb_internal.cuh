@@ -44,6 +44,7 @@ struct Control {
     unsigned long long instances_total;  // unclamped M
     unsigned long long blend_consumed;
     unsigned long long candidates_total;  // AABB instances before tile culling (the reference's M)
+    unsigned long long blend_walked;      // (warp, record) visits of the blend's inner loop (k_blend2 with stats on)
     SortCtl sort_depth;        // Gaussian-level sort (32-bit depth keys)
     SortCtl sort_tile;         // instance-level sort (tile-id keys); also used by gsb_sort_pairs
 };
@@ -127,6 +128,9 @@ struct BlendParams {
     size_t row_pitch_bytes;
     int format;             // gsb_format
     int mode;               // gsb_mode
+    int variant;            // 2 = k_blend2 (two pixels per thread, packed fp32; default), 1 = k_blend
+    int stats;              // count blend_consumed / blend_walked (costs ~4 instructions per record)
+    float one;              // 1.0f, passed as data so that ptxas cannot fold it (gsb_blend.cu, add2_of_product)
     Control* ctl;
 };
 cudaError_t launch_blend(const BlendParams& p, cudaStream_t s);

@@ -119,6 +119,8 @@ typedef struct gsb_stats {
     float sort_pass_ms[8];  /* each pass kernel of the instance sort (first sort_passes entries) */
     uint32_t sort_depth_passes; /* passes of the Gaussian-level sort (4) */
     uint32_t pad_;
+    uint64_t blend_warp_visits; /* (warp, record) visits of the blend's inner loop = evaluated pixel-pair x Gaussian work / 64
+                                   (each visit evaluates 64 pixels); counted only while timers or debug are on */
 } gsb_stats;
 
 /* ---- lifetime: replaces Renderer::initializeVulkan + create*Pipeline (Renderer.cpp:119-155,166-364) ---- */

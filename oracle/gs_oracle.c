@@ -701,6 +701,19 @@ void gso_tile_ranges(const uint64_t *keys, uint64_t m, uint32_t num_tiles, uint3
     }
 }
 
+/* Step-function probe (tests only): render.comp has two exp-dependent discontinuities per (pixel, Gaussian) pair --
+ * `alpha < 1/255` (:78) and `test_T < 0.0001` (:83).  Two valid exp implementations that differ by a few ulp can decide
+ * them differently on a pixel whose value sits on the threshold, and the image then jumps by up to alpha * T * colour
+ * (~1e-2 at worst: the break precedes the accumulate).  When a mask is installed, gso_blend marks every pixel that
+ * evaluates one of the two tests within a relative `delta` of its threshold; the 1e-4 tolerance between exp flavours
+ * (and between this oracle and any driver's exp) is asserted on the unmarked pixels, which cannot flip. */
+static uint8_t *g_probe_mask = NULL;
+static float g_probe_delta = 0.0f;
+void gso_set_step_probe(uint8_t *mask, float rel_delta) {
+    g_probe_mask = mask;
+    g_probe_delta = rel_delta;
+}
+
 /* A8. render.comp:30-99 */
 void gso_blend(const gso_attr *attr, const uint32_t *vals, const uint32_t *ranges, uint32_t width,
                uint32_t height, uint32_t tile_row_begin, uint32_t tile_row_end, float *rgba,
@@ -737,8 +750,12 @@ void gso_blend(const gso_attr *attr, const uint32_t *vals, const uint32_t *range
                         e = expf(power);
                     }
                     float alpha = fminf(0.99f, co[3] * e); /* :77 */
+                    if (g_probe_mask && fabsf(alpha - 1.0f / 255.0f) <= g_probe_delta * (1.0f / 255.0f))
+                        g_probe_mask[(size_t)py * width + px] = 1;
                     if (alpha < 1.0f / 255.0f) continue;   /* :78-80 */
                     float test_T = T * (1.0f - alpha);     /* :82 */
+                    if (g_probe_mask && fabsf(test_T - 0.0001f) <= g_probe_delta * 0.0001f)
+                        g_probe_mask[(size_t)py * width + px] = 1;
                     if (test_T < 0.0001f) break;           /* :83-85 */
                     c0 = c0 + (a->color_radii[0] * alpha) * T; /* :87 */
                     c1 = c1 + (a->color_radii[1] * alpha) * T;

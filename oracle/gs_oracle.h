@@ -63,6 +63,8 @@ typedef struct gso_synth_params { /* same fields as the product's gsh_synth_para
 } gso_synth_params;
 void gso_synth_records(uint64_t seed, uint64_t first, uint64_t n, const gso_synth_params *p, float *records);
 void gso_set_num_threads(int n);
+/* tests only: mask = H*W bytes (caller-zeroed) or NULL to switch the probe off; see gs_oracle.c */
+void gso_set_step_probe(uint8_t *mask, float rel_delta);
 void gso_set_exp_mode(int mode);
 int gso_get_exp_mode(void);
 float gso_exp_shared(float x);

@@ -198,6 +198,24 @@ def uniforms_bytes(u) -> bytes:
     return bytes(memoryview(u))[:160] if not isinstance(u, Uniforms) else bytes(u)
 
 
+lib.gso_set_step_probe.argtypes = [_vp, C.c_float]
+lib.gso_set_step_probe.restype = None
+
+
+def render_frame_probed(vertices, cov, u, rows=None, rel_delta=2e-3):
+    """render_frame + the step-function probe: returns (frame, mask) where mask[y, x] is True for pixels that evaluate
+    `alpha < 1/255` or `test_T < 1e-4` within rel_delta of the threshold (the only places where two exp flavours may
+    legitimately disagree by more than rounding noise)."""
+    ou = Uniforms.from_buffer_copy(bytes(u))
+    mask = np.zeros((ou.height, ou.width), np.uint8)
+    lib.gso_set_step_probe(mask.ctypes.data, rel_delta)
+    try:
+        f = render_frame(vertices, cov, u, rows)
+    finally:
+        lib.gso_set_step_probe(None, 0.0)
+    return f, mask.astype(bool)
+
+
 def render_frame(vertices, cov, u, rows=None, light=False) -> dict:
     """Runs the whole oracle frame; returns every intermediate as numpy arrays (light=True: counts and stage times only,
     for timing)."""

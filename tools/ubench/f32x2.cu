@@ -23,6 +23,9 @@ __global__ void k(float* out, float s) {
             if (MODE == 2) { a[i] = __fmul_rn(a[i], s); b[i] = __fadd_rn(b[i], s); }                // FMUL + FADD
             if (MODE == 3) { p[i] = mul2(p[i], ps); p[i] = add2(p[i], pc); }                        // FMUL2 + FADD2 (4 flop-pairs)
             if (MODE == 4) { p[i] = fma2(p[i], ps, pc); a[i] = __fmaf_rn(a[i], s, 1e-6f); }         // mixed
+            if (MODE == 5) p[i] = fma2(p[i], pk(0.999f, 0.999f), pk(1e-6f, 1e-6f));                  // FFMA2 with immediates
+            if (MODE == 6) p[i] = fma2(p[i], ps, p[i]);                                             // FFMA2, 2 distinct register pairs
+            if (MODE == 7) { p[i] = mul2(p[i], ps); a[i] = __fmul_rn(a[i], s); }                    // FMUL2 + FMUL
         }
     }
     float acc = 0;
@@ -40,7 +43,7 @@ void run(const char* name, double lane_ops_per_iter) {
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
     const double thr = 148.0 * 8 * 256;
     printf("%-28s %.3f ms  %.1f G lane-fp-ops/s  (%.1f G warp-instr/s)\n", name, ms, thr * ITERS * ILP * lane_ops_per_iter / ms / 1e6,
-           thr / 32 * ITERS * ILP * (MODE == 0 || MODE == 2 || MODE == 3 || MODE == 4 ? 2 : 1) / ms / 1e6);
+           thr / 32 * ITERS * ILP * (MODE == 0 || MODE == 2 || MODE == 3 || MODE == 4 || MODE == 7 ? 2 : 1) / ms / 1e6);
     cudaFree(out);
 }
 int main() {
@@ -49,5 +52,8 @@ int main() {
     run<2>("FMUL + FADD (scalar)", 2);
     run<3>("FMUL2 + FADD2 (packed)", 4);
     run<4>("FFMA2 + FFMA (mixed)", 3);
+    run<5>("1x FFMA2 (immediate b, c)", 2);
+    run<6>("1x FFMA2 (uniform b, c = a)", 2);
+    run<7>("FMUL2 + FMUL (mixed)", 3);
     return 0;
 }
