@@ -11,104 +11,17 @@
 #include <new>
 #include <vector>
 
-#include "gsb_internal.cuh"
+#include "gsb_ctx.cuh"
 
 using namespace gsb;
 
 namespace {
 thread_local std::string g_create_error;
-
-// Captured CUDA graph of the "middle" of a frame (depth sort, key emission, tile sort: 9-10 kernels whose arguments do
-// not depend on the camera).  Replaces recordRenderCommandBuffer's pre-recorded command buffer (src/Renderer.cpp:532-717).
-struct MiddleKey {
-    uint32_t tiles_x = 0, num_tiles = 0, nv_q = 0, m_q = 0, cull = 0;
-    uint64_t alloc_gen = 0;
-    bool operator==(const MiddleKey& o) const {
-        return tiles_x == o.tiles_x && num_tiles == o.num_tiles && nv_q == o.nv_q && m_q == o.m_q && cull == o.cull && alloc_gen == o.alloc_gen;
-    }
-};
-struct MiddleGraph {
-    MiddleKey key;
-    cudaGraphExec_t exec = nullptr;
-    uint64_t last_use = 0;
-};
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-};
 }  // namespace
 
-struct gsb_ctx {
-    int device = 0;
-    int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    std::string err;
+namespace gsb {
 
-    // scene
-    uint64_t n = 0;
-    float4* pos_op = nullptr;
-    float4* cov_a = nullptr;
-    float2* cov_b = nullptr;
-    float* sh = nullptr;
-
-    // frame state
-    Control* ctl = nullptr;
-    Control* ctl_host = nullptr;  // pinned mirror, filled at the end of each frame
-    uint32_t* project_status = nullptr;        // k_project look-back words (one per 256-Gaussian chunk)
-    unsigned long long* emit_status = nullptr;  // k_emit look-back words
-    float4* recs = nullptr;
-    uint2* einfo = nullptr;
-    uint32_t* dkeys[2] = {nullptr, nullptr};  // Gaussian-level sort: depth bits
-    uint32_t* dvals[2] = {nullptr, nullptr};  //                       compact ids
-    uint64_t capacity = 0;
-    uint32_t* keys[2] = {nullptr, nullptr};   // instance-level sort: tile ids
-    uint32_t* vals[2] = {nullptr, nullptr};   //                      compact ids
-    unsigned long long* sort_status = nullptr;
-    uint32_t sort_status_tiles = 0;
-    uint32_t epoch = 8;
-    uint2* ranges = nullptr;
-    uint32_t ranges_tiles = 0;
-    void* fb = nullptr;
-    size_t fb_bytes = 0;
-
-    int mode = GSB_MODE_EXACT;
-    bool debug = false;
-    bool timers = true;
-    bool tile_cull = false;
-    cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_sort[9] = {};  // instance sort: after hist, after each pass
-    cudaEvent_t ev_done = nullptr;
-    bool frame_pending = false;
-    bool have_frame = false;
-    bool frame_debug = false;   // the last frame ran with gsb_set_debug on (its debug buffers and sorted keys exist)
-    bool frame_timers = false;  // the last frame recorded the stage events (gsb_get_stats may read them)
-    bool host_direct = true;    // gsb_render to page-locked host memory: blend straight into it (GSB_HOST_DIRECT=0: always stage)
-    int blend_variant = 2;      // GSB_BLEND_VARIANT=1 selects the round-1 one-pixel-per-thread kernel (A/B only)
-    bool use_graph = true;      // replay the sorts + key emission from a captured CUDA graph when timers and debug are off
-    uint64_t alloc_gen = 0;     // bumped by every (re)allocation a captured graph could point into
-    uint64_t graph_clock = 0;
-    uint32_t frames_since_epoch_clear = 0;
-    MiddleGraph graphs[4] = {};
-    uint32_t m_hint = 0;
-    uint32_t nv_hint = 0;
-    uint32_t regrow_count = 0;
-
-    // description of the last frame (for stats / debug download)
-    uint32_t last_w = 0, last_h = 0, last_tiles_x = 0, last_tiles_y = 0, last_passes = 0, last_depth_passes = 0, last_final = 0;
-
-    // debug copies
-    uint32_t* dbg_tiles = nullptr;
-    uint4* dbg_aabb = nullptr;
-    uint32_t* dbg_keys_unsorted = nullptr;
-    uint32_t* dbg_vals_unsorted = nullptr;
-    uint64_t dbg_m = 0;
-    unsigned long long* dbg_offsets = nullptr;  // N: k_emit's exclusive scan value per depth-sorted survivor
-};
-
-namespace {
-
-int fail(gsb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+int fail(gsb_ctx* c, int code, const char* what, cudaError_t e) {
     if (c) {
         c->err = what;
         if (e != cudaSuccess) {
@@ -117,22 +30,6 @@ int fail(gsb_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
         }
     }
     return code;
-}
-
-#define CK(call)                                                       \
-    do {                                                               \
-        cudaError_t e_ = (call);                                       \
-        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? GSB_ERR_OOM : GSB_ERR_CUDA, #call, e_); \
-    } while (0)
-
-template <typename T>
-cudaError_t dev_alloc(T** p, size_t count) {
-    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(count, 1) * sizeof(T));
-}
-template <typename T>
-void dev_free(T*& p) {
-    if (p) cudaFree(p);
-    p = nullptr;
 }
 
 int free_arena(gsb_ctx* ctx) {
@@ -214,8 +111,9 @@ int wait_frame(gsb_ctx* ctx) {
     return GSB_OK;
 }
 
-__global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project_status, unsigned long long* __restrict__ emit_status,
-                             uint32_t chunks, uint2* __restrict__ ranges, uint32_t num_tiles) {
+static __global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project_status, unsigned long long* __restrict__ emit_status,
+                                    uint32_t chunks, uint2* __restrict__ ranges, uint32_t num_tiles, uint32_t* __restrict__ extra_words,
+                                    uint32_t num_extra_words) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     uint32_t* w = reinterpret_cast<uint32_t*>(ctl);
     for (uint32_t k = i; k < sizeof(Control) / 4; k += stride) {
@@ -228,27 +126,16 @@ __global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project_status
         emit_status[k] = 0ull;
     }
     for (uint32_t k = i; k < num_tiles; k += stride) ranges[k] = make_uint2(0xffffffffu, 0xffffffffu);  // tile_boundary's fillBuffer (Renderer.cpp:633)
+    for (uint32_t k = i; k < num_extra_words; k += stride) extra_words[k] = 0u;  // frame sharding: k_route's look-back words
 }
 
-}  // namespace
-
-namespace gsb {
 cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, unsigned long long* emit_status, uint32_t chunks,
-                              uint2* ranges, uint32_t num_tiles, cudaStream_t s) {
-    const uint32_t work = std::max<uint32_t>(std::max(chunks, num_tiles), (uint32_t)(sizeof(Control) / 4));
+                              uint2* ranges, uint32_t num_tiles, cudaStream_t s, uint32_t* extra_words, uint32_t num_extra_words) {
+    const uint32_t work = std::max<uint32_t>(std::max(std::max(chunks, num_tiles), num_extra_words), (uint32_t)(sizeof(Control) / 4));
     const uint32_t blocks = std::min<uint32_t>((work + 255) / 256, 148u * 4u);
-    k_frame_init<<<blocks, 256, 0, s>>>(ctl, project_status, emit_status, chunks, ranges, num_tiles);
+    k_frame_init<<<blocks, 256, 0, s>>>(ctl, project_status, emit_status, chunks, ranges, num_tiles, extra_words, num_extra_words);
     return cudaGetLastError();
 }
-}  // namespace gsb
-
-namespace {
-
-struct FramePlan {
-    uint32_t W, H, tiles_x, tiles_y, T, rb, re;
-    uint32_t nv_q, m_q, depth_passes, passes;
-    int fin;
-};
 
 // depth sort -> key emission -> tile sort: everything between k_project and k_blend.  No argument depends on the camera,
 // so the sequence is captured once per (frame size, grid sizes, allocation generation) and replayed.
@@ -280,7 +167,6 @@ int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool 
     // ---- k_emit: scan of tile counts + (tile id, payload) emission in depth order ----
     EmitParams ep{};
     ep.sorted_cid = ctx->dvals[fin_a];
-    ep.einfo = ctx->einfo;
     ep.nv_hint = fp.nv_q;
     ep.tiles_x = fp.tiles_x;
     ep.keys = ctx->keys[0];
@@ -344,6 +230,7 @@ int launch_middle_graph(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) 
     key.nv_q = fp.nv_q;
     key.m_q = fp.m_q;
     key.cull = ctx->tile_cull ? 1u : 0u;
+    key.tag = ctx->middle_tag;
     key.alloc_gen = ctx->alloc_gen;
     MiddleGraph* slot = nullptr;
     for (auto& g : ctx->graphs)
@@ -377,8 +264,7 @@ int launch_middle_graph(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) 
     return GSB_OK;
 }
 
-// frame start + k_project + middle.  After this the tile ranges and sorted payloads of the frame are in flight on `stream`.
-int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, cudaStream_t stream, FramePlan* out) {
+int plan_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, cudaStream_t stream, FramePlan* out) {
     FramePlan fp{};
     fp.W = ubo->width;
     fp.H = ubo->height;
@@ -394,18 +280,27 @@ int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
         ctx->ranges_tiles = fp.T;
     }
     const uint32_t n = (uint32_t)ctx->n;
-    const uint32_t chunks = (n + 255) / 256;
     fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : n), quantise_hint(n));
     fp.m_q = quantise_hint(ctx->m_hint ? ctx->m_hint : std::min<uint64_t>(ctx->capacity, 4u * 1024 * 1024));
     fp.depth_passes = 4;
     fp.passes = (bits_for(fp.T) + 7) / 8;
     fp.fin = (int)(fp.passes & 1);
-
     if (++ctx->frames_since_epoch_clear >= (1u << 27)) {  // epoch wrap (2^32 / 16 frames): clear the look-back tags once
         CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
         CK(cudaMemsetAsync(&ctx->ctl->epoch, 0, sizeof(uint32_t), stream));
         ctx->frames_since_epoch_clear = 0;
     }
+    *out = fp;
+    return GSB_OK;
+}
+
+// frame start + k_project + middle.  After this the tile ranges and sorted payloads of the frame are in flight on `stream`.
+static int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, cudaStream_t stream, FramePlan* out) {
+    FramePlan fp{};
+    int rc = plan_frame(ctx, ubo, rb, re, stream, &fp);
+    if (rc != GSB_OK) return rc;
+    const uint32_t n = (uint32_t)ctx->n;
+    const uint32_t chunks = (n + 255) / 256;
     const bool timers = ctx->timers;
     CK(launch_frame_init(ctx->ctl, ctx->project_status, ctx->emit_status, std::max(chunks, 1u), ctx->ranges, fp.T, stream));
     if (timers) CK(cudaEventRecord(ctx->ev[0], stream));
@@ -417,11 +312,11 @@ int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     pp.cov_b = ctx->cov_b;
     pp.sh = ctx->sh;
     pp.n = n;
+    pp.index_base = 0;
     pp.ubo = *ubo;
     pp.tile_row_begin = rb;
     pp.tile_row_end = re;
     pp.recs = ctx->recs;
-    pp.einfo = ctx->einfo;
     pp.dkeys = ctx->dkeys[0];
     pp.dvals = ctx->dvals[0];
     pp.status = ctx->project_status;
@@ -431,7 +326,6 @@ int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
     CK(launch_project(pp, ctx->debug, stream));
     if (timers) CK(cudaEventRecord(ctx->ev[1], stream));
 
-    int rc;
     if (ctx->use_graph && !timers && !ctx->debug) rc = launch_middle_graph(ctx, fp, stream);
     else rc = enqueue_middle(ctx, fp, stream, timers);
     if (rc != GSB_OK) return rc;
@@ -441,7 +335,7 @@ int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t r
 
 // k_blend over tile rows [b0, b1) of the frame; `band_out` is the first pixel row of the frame's band [fp.rb, fp.re).
 int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, void* band_out, size_t pitch, int fmt,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, void* const* peer_frames, int num_peer_frames) {
     BlendParams bp{};
     bp.recs = ctx->recs;
     bp.vals = ctx->vals[fp.fin];
@@ -452,6 +346,11 @@ int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, v
     bp.tile_row_begin = b0;
     bp.tile_row_end = b1;
     bp.out = static_cast<unsigned char*>(band_out) + (size_t)(b0 - fp.rb) * GSB_TILE * pitch;
+    bp.out_first_row = b0 * GSB_TILE;
+    // frame sharding: the band is stored into the WHOLE-frame buffers of every rank (peer memory over NVLink) instead
+    bp.num_peers = num_peer_frames;
+    for (int k = 0; k < num_peer_frames && k < GSB_MAX_SHARDS; k++) bp.peer_frames[k] = peer_frames[k];
+    if (num_peer_frames > 0) bp.out_first_row = 0;
     bp.row_pitch_bytes = pitch;
     bp.format = fmt;
     bp.mode = ctx->mode;
@@ -483,7 +382,7 @@ int enqueue_tail(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) {
 }
 
 // Enqueue one whole frame on `stream`; out_dev is device memory.
-int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out_dev, size_t pitch, int fmt,
+static int enqueue_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, void* out_dev, size_t pitch, int fmt,
                   cudaStream_t stream) {
     FramePlan fp{};
     int rc = enqueue_front(ctx, ubo, rb, re, stream, &fp);
@@ -510,7 +409,7 @@ int check_render_args(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t& rb, uint3
     return GSB_OK;
 }
 
-}  // namespace
+}  // namespace gsb
 
 extern "C" {
 
@@ -584,6 +483,7 @@ void gsb_destroy(gsb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaDeviceSynchronize();
     drop_graphs(ctx);
+    shard_destroy(ctx);
     dev_free(ctx->dbg_offsets);
     dev_free(ctx->pos_op);
     dev_free(ctx->cov_a);
@@ -594,7 +494,6 @@ void gsb_destroy(gsb_ctx* ctx) {
     dev_free(ctx->project_status);
     dev_free(ctx->emit_status);
     dev_free(ctx->recs);
-    dev_free(ctx->einfo);
     dev_free(ctx->dkeys[0]);
     dev_free(ctx->dkeys[1]);
     dev_free(ctx->dvals[0]);
@@ -628,7 +527,6 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     dev_free(ctx->cov_b);
     dev_free(ctx->sh);
     dev_free(ctx->recs);
-    dev_free(ctx->einfo);
     dev_free(ctx->dkeys[0]);
     dev_free(ctx->dkeys[1]);
     dev_free(ctx->dvals[0]);
@@ -645,8 +543,7 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     CK(dev_alloc(&ctx->cov_a, n));
     CK(dev_alloc(&ctx->cov_b, n));
     CK(dev_alloc(&ctx->sh, n * 48));
-    CK(dev_alloc(&ctx->recs, n * 3));
-    CK(dev_alloc(&ctx->einfo, n));
+    CK(dev_alloc(&ctx->recs, n * GSB_REC_F4));
     CK(dev_alloc(&ctx->dkeys[0], n));
     CK(dev_alloc(&ctx->dkeys[1], n));
     CK(dev_alloc(&ctx->dvals[0], n));
@@ -946,33 +843,34 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
             return GSB_OK;
         }
         case GSB_BUF_ATTR: {
-            std::vector<float4> recs((size_t)nv * 3);
+            std::vector<float4> recs((size_t)nv * GSB_REC_F4);
             std::vector<uint4> aabb(n);
             if (nv) CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
             if (n) CK(cudaMemcpy(aabb.data(), ctx->dbg_aabb, n * sizeof(uint4), cudaMemcpyDeviceToHost));
             gsb_vertex_attribute* o = static_cast<gsb_vertex_attribute*>(dst);
             memset(o, 0, n * sizeof(gsb_vertex_attribute));
             for (uint32_t c = 0; c < nv; c++) {
-                const float4 r0 = recs[(size_t)c * 3], r1 = recs[(size_t)c * 3 + 1], r2 = recs[(size_t)c * 3 + 2];
+                const float4 r0 = recs[(size_t)c * GSB_REC_F4], r1 = recs[(size_t)c * GSB_REC_F4 + 1], r2 = recs[(size_t)c * GSB_REC_F4 + 2],
+                             r3 = recs[(size_t)c * GSB_REC_F4 + 3];
                 uint32_t i;
-                memcpy(&i, &r2.w, 4);
+                memcpy(&i, &r3.y, 4);
                 if (i >= n) return fail(ctx, GSB_ERR_CUDA, "corrupt compact record");
                 gsb_vertex_attribute& a = o[i];
                 a.conic_opacity[0] = r0.z;
                 a.conic_opacity[1] = r0.w;
                 a.conic_opacity[2] = r1.x;
                 a.conic_opacity[3] = r1.y;
-                a.color_radii[0] = r1.z;
-                a.color_radii[1] = r1.w;
-                a.color_radii[2] = r2.x;
-                a.color_radii[3] = r2.z;
+                a.color_radii[0] = r2.x;
+                a.color_radii[1] = r2.y;
+                a.color_radii[2] = r2.z;
+                a.color_radii[3] = r3.x;
                 a.aabb[0] = aabb[i].x;
                 a.aabb[1] = aabb[i].y;
                 a.aabb[2] = aabb[i].z;
                 a.aabb[3] = aabb[i].w;
                 a.uv[0] = r0.x;
                 a.uv[1] = r0.y;
-                a.depth = r2.y;
+                a.depth = r2.w;
                 a.magic = 0x4d415449u;  // common.glsl:14
             }
             return GSB_OK;
@@ -997,7 +895,7 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
             // device pairs are (u32 tile id, u32 compact id); rebuild the reference's (tile << 32 | depth, Gaussian index)
             const bool sorted = which == GSB_BUF_KEYS_SORTED || which == GSB_BUF_VALS_SORTED;
             const bool want_keys = which == GSB_BUF_KEYS_UNSORTED || which == GSB_BUF_KEYS_SORTED;
-            std::vector<float4> recs((size_t)nv * 3);
+            std::vector<float4> recs((size_t)nv * GSB_REC_F4);
             if (nv) CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
             std::vector<uint32_t> tk(m), cv(m);
             const uint32_t* ksrc = sorted ? ctx->keys[ctx->last_final] : ctx->dbg_keys_unsorted;
@@ -1008,17 +906,17 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
             }
             for (uint64_t k = 0; k < m; k++) {
                 if (cv[k] >= nv) return fail(ctx, GSB_ERR_CUDA, "corrupt payload");
-                const float4 r2 = recs[(size_t)cv[k] * 3 + 2];
+                const float4 r2 = recs[(size_t)cv[k] * GSB_REC_F4 + 2], r3 = recs[(size_t)cv[k] * GSB_REC_F4 + 3];
                 uint32_t depth_bits, orig;
-                memcpy(&depth_bits, &r2.y, 4);
-                memcpy(&orig, &r2.w, 4);
+                memcpy(&depth_bits, &r2.w, 4);
+                memcpy(&orig, &r3.y, 4);
                 if (want_keys) static_cast<uint64_t*>(dst)[k] = ((uint64_t)tk[k] << 32) | depth_bits;
                 else static_cast<uint32_t*>(dst)[k] = orig;
             }
             return GSB_OK;
         }
         case GSB_BUF_DEPTH_ORDER: {  // the Gaussian-level sort's output: survivors in (depth bits, index) order, as Gaussian indices
-            std::vector<float4> recs((size_t)nv * 3);
+            std::vector<float4> recs((size_t)nv * GSB_REC_F4);
             std::vector<uint32_t> cid(nv);
             if (nv) {
                 CK(cudaMemcpy(recs.data(), ctx->recs, recs.size() * sizeof(float4), cudaMemcpyDeviceToHost));
@@ -1026,7 +924,7 @@ int gsb_debug_download(gsb_ctx* ctx, gsb_buffer which, void* dst, size_t bytes) 
             }
             for (uint32_t j = 0; j < nv; j++) {
                 if (cid[j] >= nv) return fail(ctx, GSB_ERR_CUDA, "corrupt depth order");
-                memcpy(static_cast<uint32_t*>(dst) + j, &recs[(size_t)cid[j] * 3 + 2].w, 4);
+                memcpy(static_cast<uint32_t*>(dst) + j, &recs[(size_t)cid[j] * GSB_REC_F4 + 3].y, 4);
             }
             return GSB_OK;
         }

@@ -149,12 +149,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
         const uint32_t cnt = min((uint32_t)BLEND_THREADS, range.y - base);
         if ((uint32_t)tid < cnt) {
             const uint32_t cid = __ldg(P.vals + base + tid);
-            const float4* rec = P.recs + (size_t)cid * 3;
-            const float4 a = __ldg(rec), b = __ldg(rec + 1);
+            const float4* rec = P.recs + (size_t)cid * GSB_REC_F4;
+            const float4 a = __ldg(rec), col = __ldg(rec + 2);
+            const float2 b = __ldg(reinterpret_cast<const float2*>(rec + 1));  // conic.z, opacity
             const float cut = power_cut(b.y);
             s_rec[tid].r0 = make_float4(a.x, a.y, -0.5f * a.z, -a.w);
-            s_rec[tid].r1 = make_float4(-0.5f * b.x, cut, b.y, b.z);
-            s_rec[tid].r2 = make_float4(b.w, __ldg(reinterpret_cast<const float*>(rec + 2)), 0.f, 0.f);
+            s_rec[tid].r1 = make_float4(-0.5f * b.x, cut, b.y, col.x);
+            s_rec[tid].r2 = make_float4(col.y, col.z, 0.f, 0.f);
             s_mask[tid] = block_mask(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
         }
         __syncthreads();
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSB_BLEND_MIN_BLOCKS) k_blend(c
 
     if (inside) {
         atomicMax(&s_used, used);
-        const uint32_t row = py - P.tile_row_begin * GSB_TILE;
+        const uint32_t row = py - P.out_first_row;
         unsigned char* dst = static_cast<unsigned char*>(P.out) + (size_t)row * P.row_pitch_bytes;
         if (P.format == GSB_FORMAT_RGBA32F) {
             reinterpret_cast<float4*>(dst)[px] = make_float4(c0, c1, c2, 1.0f);  // :98 vec4(c, 1)
@@ -328,7 +329,10 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
 //                        with a uniform-register operand;
 //   GSB_BLEND2_ADD == 0: two scalar add.rn.f32 on the halves.
 #ifndef GSB_BLEND2_ADD
-#define GSB_BLEND2_ADD 1
+#define GSB_BLEND2_ADD 0  // measured on the bench scene: k_blend2 0.597 ms with the scalar adds, 0.665 ms with FFMA2 (half-rate on B200)
+#endif
+#ifndef GSB_BLEND2_PRED
+#define GSB_BLEND2_PRED 1  // colour / transmittance updates: 1 = predicated scalar adds, 0 = packed adds + selects
 #endif
 __device__ __forceinline__ u64 add2_of_product(u64 prod, u64 b, u64 one2) {
 #if GSB_BLEND2_ADD
@@ -424,8 +428,9 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     }
     __syncthreads();
 
-    float T0 = 1.0f, T1 = 1.0f, ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f, cc0 = 0.f, cc1 = 0.f;  // colour a/b/c of pixel 0/1
-    bool done0 = !in0, done1 = !in1;
+    // transmittance (0 = finished or outside the image) and colour a/b/c of pixel 0/1
+    float T0 = in0 ? 1.0f : 0.0f, T1 = in1 ? 1.0f : 0.0f, ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f, cc0 = 0.f, cc1 = 0.f;
+#define B2_DONE (T0 == 0.0f && T1 == 0.0f)
     uint32_t used = 0, walked = 0;
     const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);
     const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
@@ -437,21 +442,21 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             const uint32_t li = (uint32_t)(j * B2_THREADS + tid);
             if (li < cnt) {
                 const uint32_t cid = __ldg(P.vals + base + li);
-                const float4* rec = P.recs + (size_t)cid * 3;
-                const float4 a = __ldg(rec), b = __ldg(rec + 1);
-                const float cb = __ldg(reinterpret_cast<const float*>(rec + 2));
+                const float4* rec = P.recs + (size_t)cid * GSB_REC_F4;
+                const float4 a = __ldg(rec), col = __ldg(rec + 2);
+                const float2 b = __ldg(reinterpret_cast<const float2*>(rec + 1));  // conic.z, opacity
                 const float cut = power_cut(b.y);
                 const float na = -0.5f * a.z, nb = -a.w, nc = -0.5f * b.x;
                 s_rec[li].q0 = make_float4(a.x, a.x, a.y, a.y);
                 s_rec[li].q1 = make_float4(na, na, nb, nb);
                 s_rec[li].q2 = make_float4(nc, nc, b.y, b.y);
-                s_rec[li].q3 = make_float4(b.z, b.z, b.w, b.w);
-                s_rec[li].q4 = make_float4(cb, cb, cut, __uint_as_float(li));
+                s_rec[li].q3 = make_float4(col.x, col.x, col.y, col.y);
+                s_rec[li].q4 = make_float4(col.z, col.z, cut, __uint_as_float(li));
                 s_mask[li] = (uint8_t)block_mask2(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
             }
         }
         __syncthreads();
-        if (!__all_sync(FULL, done0 && done1)) {
+        if (!__all_sync(FULL, B2_DONE)) {
             uint32_t n = 0;
             for (uint32_t c = 0; c < cnt; c += 32) {  // one ballot per 32 records
                 const bool mine = (c + lane < cnt) && ((s_mask[c + lane] >> warp) & 1u);
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             const uint32_t base_off = base - range.x;
             uint32_t k0 = 0;
             for (; k0 < n; k0 += GSB_BLEND2_CHECK) {
-                if (__all_sync(FULL, done0 && done1)) break;
+                if (__all_sync(FULL, B2_DONE)) break;
                 const uint32_t k1 = min(n, k0 + (uint32_t)GSB_BLEND2_CHECK);
                 for (uint32_t k = k0; k < k1; k++) {
                     const uint32_t addr = lds_u16(list_sh + 2u * k);
@@ -498,21 +503,46 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
                         al1 = fminf(0.99f, o1 * __expf(pw1));
                     }
                     alpha2 = pk2(al0, al1);
-                    // :68-70 and, below the Gaussian's cut, alpha < 1/255 (:78); a NaN power passes like in the shader
-                    bool ok0 = !done0 && !(pw0 > 0.0f || pw0 < cut) && !(al0 < 1.0f / 255.0f);  // :78-80
-                    bool ok1 = !done1 && !(pw1 > 0.0f || pw1 < cut) && !(al1 < 1.0f / 255.0f);
+                    // A finished (or out-of-image) pixel carries T == 0 (a live one has T >= 1e-4): its test_T is 0, so it
+                    // "finishes" again at every record it would touch, never accumulates, and needs no separate flag.
+                    // in0 / in1: :68-70 and, below the Gaussian's cut, alpha < 1/255 (:78); a NaN power passes like in the shader
+                    const bool in0k = !(pw0 > 0.0f || pw0 < cut) && !(al0 < 1.0f / 255.0f);  // :78-80
+                    const bool in1k = !(pw1 > 0.0f || pw1 < cut) && !(al1 < 1.0f / 255.0f);
                     float tt0, tt1;
                     const u64 T2 = pk2(T0, T1);
                     upk2(mul2(T2, sub2(pk2(1.0f, 1.0f), alpha2)), tt0, tt1);  // :82
-                    const bool fin0 = ok0 && tt0 < 0.0001f, fin1 = ok1 && tt1 < 0.0001f;  // :83-85
-                    done0 = done0 || fin0;
-                    done1 = done1 || fin1;
-                    ok0 = ok0 && !fin0;
-                    ok1 = ok1 && !fin1;
+                    const bool ok0 = in0k && !(tt0 < 0.0001f), ok1 = in1k && !(tt1 < 0.0001f);  // :83-85 (the break)
                     if (STATS) {
                         const uint32_t u = base_off + __float_as_uint(idxf) + 1u;
-                        used = (fin0 || fin1) ? max(used, u) : used;
+                        used = ((in0k && !ok0 && T0 != 0.0f) || (in1k && !ok1 && T1 != 0.0f)) ? max(used, u) : used;
                     }
+#if GSB_BLEND2_PRED
+                    // predicated scalar accumulates (FMA pipe) instead of packed adds + selects (the half-rate ALU pipe is
+                    // this kernel's bottleneck: profiles/)
+                    float w0a, w1a, w0b, w1b, w0c, w1c;
+                    if (MODE == GSB_MODE_EXACT) {
+                        upk2(mul2(mul2(r2, alpha2), T2), w0a, w1a);  // :87
+                        upk2(mul2(mul2(g2, alpha2), T2), w0b, w1b);
+                        upk2(mul2(mul2(b2, alpha2), T2), w0c, w1c);
+                    } else {
+                        const u64 w2 = mul2(alpha2, T2);
+                        upk2(mul2(r2, w2), w0a, w1a);
+                        upk2(mul2(g2, w2), w0b, w1b);
+                        upk2(mul2(b2, w2), w0c, w1c);
+                    }
+                    if (ok0) {
+                        ca0 = __fadd_rn(ca0, w0a);
+                        cb0 = __fadd_rn(cb0, w0b);
+                        cc0 = __fadd_rn(cc0, w0c);
+                    }
+                    if (ok1) {
+                        ca1 = __fadd_rn(ca1, w1a);
+                        cb1 = __fadd_rn(cb1, w1b);
+                        cc1 = __fadd_rn(cc1, w1c);
+                    }
+                    if (in0k) T0 = ok0 ? tt0 : 0.0f;  // :88, or the break
+                    if (in1k) T1 = ok1 ? tt1 : 0.0f;
+#else
                     float na0, na1, nb0, nb1, nc0, nc1;
                     if (MODE == GSB_MODE_EXACT) {
                         upk2(add2_of_product(mul2(mul2(r2, alpha2), T2), pk2(ca0, ca1), one2), na0, na1);  // :87
@@ -527,30 +557,37 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
                     ca0 = ok0 ? na0 : ca0;
                     cb0 = ok0 ? nb0 : cb0;
                     cc0 = ok0 ? nc0 : cc0;
-                    T0 = ok0 ? tt0 : T0;  // :88
+                    T0 = in0k ? (ok0 ? tt0 : 0.0f) : T0;  // :88, or the break
                     ca1 = ok1 ? na1 : ca1;
                     cb1 = ok1 ? nb1 : cb1;
                     cc1 = ok1 ? nc1 : cc1;
-                    T1 = ok1 ? tt1 : T1;
+                    T1 = in1k ? (ok1 ? tt1 : 0.0f) : T1;
+#endif
                 }
             }
             if (STATS) {
                 walked += min(k0, n);
-                if (!(done0 && done1)) used = base_off + cnt;  // a live pixel read the whole batch
+                if (!B2_DONE) used = base_off + cnt;  // a live pixel read the whole batch
             }
         }
-        if (__syncthreads_and(done0 && done1)) break;
+        if (__syncthreads_and(B2_DONE)) break;
     }
+#undef B2_DONE
 
     if (STATS) {
         if (in0 || in1) atomicMax(&s_used, used);
         if (lane == 0 && walked) atomicAdd(&s_walked, walked);
     }
-    unsigned char* band = static_cast<unsigned char*>(P.out);
-    const uint32_t row0 = py0 - P.tile_row_begin * GSB_TILE;
+    // Destinations: the caller's buffer, or -- frame sharding -- the whole-frame buffer of EVERY rank (peer memory over
+    // NVLink; posted stores, so the framebuffer exchange rides under the blend instead of following it as a collective).
+    const int ndst = P.num_peers > 0 ? P.num_peers : 1;
+    const uint32_t row0 = py0 - P.out_first_row;
     if (P.format == GSB_FORMAT_RGBA32F) {
-        if (in0) reinterpret_cast<float4*>(band + (size_t)row0 * P.row_pitch_bytes)[px] = make_float4(ca0, cb0, cc0, 1.0f);  // :98 vec4(c, 1)
-        if (in1) reinterpret_cast<float4*>(band + (size_t)(row0 + 4) * P.row_pitch_bytes)[px] = make_float4(ca1, cb1, cc1, 1.0f);
+        for (int d = 0; d < ndst; d++) {
+            unsigned char* band = static_cast<unsigned char*>(P.num_peers > 0 ? P.peer_frames[d] : P.out);
+            if (in0) reinterpret_cast<float4*>(band + (size_t)row0 * P.row_pitch_bytes)[px] = make_float4(ca0, cb0, cc0, 1.0f);  // :98 vec4(c, 1)
+            if (in1) reinterpret_cast<float4*>(band + (size_t)(row0 + 4) * P.row_pitch_bytes)[px] = make_float4(ca1, cb1, cc1, 1.0f);
+        }
     } else {
         // 8-bit formats: transpose the tile through shared memory so that every warp store covers whole 64-B tile rows
         // (also what lets gsb_render write a pinned host frame directly at a good PCIe payload size)
@@ -568,13 +605,16 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             const uint32_t ry = (uint32_t)tid >> 2, rx = ((uint32_t)tid & 3u) * 4u;
             const uint32_t gy = ty * GSB_TILE + ry, gx = tx * GSB_TILE + rx;
             if (gy < P.height && gx < P.width) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(band + (size_t)(gy - P.tile_row_begin * GSB_TILE) * P.row_pitch_bytes) + gx;
                 const uint4 v = *reinterpret_cast<const uint4*>(&s_tile[ry * 16 + rx]);
-                if (gx + 3 < P.width && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-                    *reinterpret_cast<uint4*>(dst) = v;
-                } else {  // ragged right edge (W not a multiple of 4) or an unaligned pitch
-                    const uint32_t e[4] = {v.x, v.y, v.z, v.w};
-                    for (uint32_t q = 0; q < 4 && gx + q < P.width; q++) dst[q] = e[q];
+                for (int d = 0; d < ndst; d++) {
+                    unsigned char* band = static_cast<unsigned char*>(P.num_peers > 0 ? P.peer_frames[d] : P.out);
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(band + (size_t)(gy - P.out_first_row) * P.row_pitch_bytes) + gx;
+                    if (gx + 3 < P.width && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+                        *reinterpret_cast<uint4*>(dst) = v;
+                    } else {  // ragged right edge (W not a multiple of 4) or an unaligned pitch
+                        const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+                        for (uint32_t q = 0; q < 4 && gx + q < P.width; q++) dst[q] = e[q];
+                    }
                 }
             }
         }
@@ -594,7 +634,7 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t s) {
     const uint32_t rows = p.tile_row_end - p.tile_row_begin;
     const uint32_t blocks = rows * p.tiles_x;
     if (blocks == 0) return cudaSuccess;
-    if (p.variant == 1) {  // round-1 kernel (one pixel per thread), kept for A/B: GSB_BLEND_VARIANT=1
+    if (p.variant == 1 && p.num_peers == 0) {  // round-1 kernel (one pixel per thread), kept for A/B: GSB_BLEND_VARIANT=1
         if (p.mode == GSB_MODE_EXACT) k_blend<GSB_MODE_EXACT><<<blocks, BLEND_THREADS, 0, s>>>(p);
         else k_blend<GSB_MODE_FAST><<<blocks, BLEND_THREADS, 0, s>>>(p);
     } else if (p.stats) {

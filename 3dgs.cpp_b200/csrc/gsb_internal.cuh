@@ -5,11 +5,11 @@
 //           cov_a[N]   float4 (S00, S01, S02, S11)          16 B
 //           cov_b[N]   float2 (S12, S22)                     8 B
 //           sh[N][48]  RGB-interleaved degree-3 SH         192 B  read by cull survivors only
-//   frame   recs[Nv][3] float4  compacted per-survivor blend record (48 B):
-//               r0 = (uv.x, uv.y, conic.x, conic.y)
-//               r1 = (conic.z, opacity, color.r, color.g)
-//               r2 = (color.b, depth, radius, bits(original index))
-//           einfo[Nv]  uint2 (x0 | y0 << 16, w | h << 16) tile AABB of the survivor
+//   frame   recs[Nv][4] float4  compacted per-survivor record, 64 B, 64-B aligned (GSB_REC_F4 float4):
+//               q0 = (uv.x, uv.y, conic.x, conic.y)                  \ first 32-B sector: all k_emit reads
+//               q1 = (conic.z, opacity, bits(x0 | y0 << 16), bits(w | h << 16))  / (tile AABB, band-clipped)
+//               q2 = (color.r, color.g, color.b, depth)              the blend reads q0, q1.xy, q2.xyz
+//               q3 = (radius, bits(original index), -, -)            debug downloads only
 //           dkeys[2][Nv] u32 bits(depth), dvals[2][Nv] u32 compact id      -- Gaussian-level sort
 //           keys[2][cap] u32 tile id,     vals[2][cap] u32 compact id      -- instance-level sort
 //           ranges[T] uint2 (start, ~end) per tile; (0xFFFFFFFF, 0xFFFFFFFF) = empty
@@ -22,6 +22,8 @@
 #include "gs_b200.h"
 
 #define GSB_TILE 16
+#define GSB_REC_F4 4  // float4 per survivor record
+#define GSB_MAX_SHARDS 8  // GPUs of one NVSwitch domain a frame can be sharded over
 
 namespace gsb {
 
@@ -47,6 +49,9 @@ struct Control {
     unsigned long long blend_walked;      // (warp, record) visits of the blend's inner loop (k_blend2 with stats on)
     SortCtl sort_depth;        // Gaussian-level sort (32-bit depth keys)
     SortCtl sort_tile;         // instance-level sort (tile-id keys); also used by gsb_sort_pairs
+    // frame sharding (gsb_shard.cu): k_route's chunk tickets and per-destination-band survivor totals
+    uint32_t route_ticket;
+    uint32_t route_total[GSB_MAX_SHARDS];
 };
 
 struct ProjectParams {
@@ -55,11 +60,11 @@ struct ProjectParams {
     const float2* cov_b;
     const float* sh;
     uint32_t n;
+    uint32_t index_base;  // global index of this context's first Gaussian (frame sharding: the rank's slice; else 0)
     gsb_uniforms ubo;
     uint32_t tile_row_begin, tile_row_end;  // band clip (multi-GPU); [0, tiles_y) = whole frame
     // outputs (compacted by survivor rank)
     float4* recs;
-    uint2* einfo;
     uint32_t* dkeys;
     uint32_t* dvals;
     uint32_t* status;  // decoupled look-back words, one per 256-Gaussian chunk
@@ -71,7 +76,6 @@ struct ProjectParams {
 
 struct EmitParams {
     const uint32_t* sorted_cid;  // survivors in (depth, index) order
-    const uint2* einfo;
     uint32_t nv_hint;            // host estimate of N_v (sizes the grid only)
     uint32_t tiles_x;
     uint32_t* keys;              // tile ids
@@ -80,7 +84,7 @@ struct EmitParams {
     unsigned long long* status;  // decoupled look-back words, one per 256-survivor chunk
     Control* ctl;
     int num_sms;
-    const float4* recs;          // blend records (centre + conic) for the optional instance culling
+    const float4* recs;          // survivor records: tile AABB (+ centre, conic, opacity for the optional instance culling)
     int cull;                    // gsb_set_tile_cull
     unsigned long long* dbg_offsets;  // debug (may be null): exclusive instance offset of each depth-sorted survivor
 };
@@ -114,7 +118,8 @@ uint32_t sort_tile_items();
 // One kernel instead of four memsets: zeroes the control block (keeping overflow_sticky) and the look-back words of
 // k_project / k_emit, and fills the tile ranges with (0xFFFFFFFF, 0xFFFFFFFF) = empty.
 cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, unsigned long long* emit_status, uint32_t chunks,
-                              uint2* ranges, uint32_t num_tiles, cudaStream_t s);
+                              uint2* ranges, uint32_t num_tiles, cudaStream_t s, uint32_t* extra_words = nullptr,
+                              uint32_t num_extra_words = 0);
 cudaError_t sort_prepare();  // one-time function attributes (dynamic shared memory opt-in) of the Onesweep kernels
 cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaStream_t s);
 
@@ -124,7 +129,10 @@ struct BlendParams {
     const uint2* ranges;
     uint32_t width, height, tiles_x;
     uint32_t tile_row_begin, tile_row_end;
-    void* out;              // first pixel row of the band
+    void* out;              // pixel row `out_first_row` of the frame lives at out + 0
+    uint32_t out_first_row; // 16 * tile_row_begin for a band buffer, 0 for a whole-frame buffer
+    int num_peers;          // > 0: store the band into these whole-frame buffers instead of `out` (one per rank, peer memory)
+    void* peer_frames[GSB_MAX_SHARDS];
     size_t row_pitch_bytes;
     int format;             // gsb_format
     int mode;               // gsb_mode

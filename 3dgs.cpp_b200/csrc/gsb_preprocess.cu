@@ -280,11 +280,12 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
     // ---- compacted per-survivor outputs ----
     if (surv) {
         const uint32_t cid = s_base_surv + surv_before + surv_rank_w;
-        float4* rec = P.recs + (size_t)cid * 3;
+        float4* rec = P.recs + (size_t)cid * GSB_REC_F4;
         rec[0] = make_float4(uvx, uvy, conx, cony);
-        rec[1] = make_float4(conz, opac, colr, colg);
-        rec[2] = make_float4(colb, depth, radii, __uint_as_float(i));
-        P.einfo[cid] = make_uint2((uint32_t)bx0 | ((uint32_t)by0 << 16), (uint32_t)(bx1 - bx0) | ((uint32_t)(by1 - by0) << 16));
+        rec[1] = make_float4(conz, opac, __uint_as_float((uint32_t)bx0 | ((uint32_t)by0 << 16)),
+                             __uint_as_float((uint32_t)(bx1 - bx0) | ((uint32_t)(by1 - by0) << 16)));
+        rec[2] = make_float4(colr, colg, colb, depth);
+        rec[3] = make_float4(radii, __uint_as_float(P.index_base + i), 0.f, 0.f);  // global Gaussian index (the sort payload of the reference)
         P.dkeys[cid] = __float_as_uint(depth);  // depth > 0.2: the IEEE bits are monotone as unsigned
         P.dvals[cid] = cid;
     }
@@ -334,9 +335,9 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
         uint32_t nt = 0, cid = 0, xy = 0, wh = 0;
         if (j < nv) {
             cid = __ldg(P.sorted_cid + j);
-            const uint2 inf = __ldg(P.einfo + cid);
-            xy = inf.x;
-            wh = inf.y;
+            const float4 q1 = __ldg(P.recs + (size_t)cid * GSB_REC_F4 + 1);
+            xy = __float_as_uint(q1.z);
+            wh = __float_as_uint(q1.w);
             nt = (wh & 0xffffu) * (wh >> 16);
         }
         // ---- block scan of the tile counts (prefix_sum.comp's job) ----
@@ -586,18 +587,19 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_EMIT_MIN_BLOCKS) k_emit_cull(
         CullGauss g{};
         if (j < nv) {
             cid = __ldg(P.sorted_cid + j);
-            const uint2 inf = __ldg(P.einfo + cid);
-            xy = inf.x;
-            wh = inf.y;
+            const float4 q1 = __ldg(P.recs + (size_t)cid * GSB_REC_F4 + 1);  // conic.z, opacity, AABB: same 32-B sector as q0
+            xy = __float_as_uint(q1.z);
+            wh = __float_as_uint(q1.w);
             cand = (wh & 0xffffu) * (wh >> 16);
             nt = cand;
             if (cand != 0 && cand <= EMIT_BIG) {
-                const float4 r0 = __ldg(P.recs + (size_t)cid * 3);
-                const float2 co = __ldg(reinterpret_cast<const float2*>(P.recs + (size_t)cid * 3 + 1));  // conic.z, opacity
-                const float cc = co.x;
-                const float radius = __ldg(reinterpret_cast<const float*>(P.recs + (size_t)cid * 3 + 2) + 2);
-                const float reach = radius + 32.0f;  // |uv - pixel| inside the AABB's tiles
-                g = cull_setup(r0, cc, co.y, reach, reach);
+                const float4 r0 = __ldg(P.recs + (size_t)cid * GSB_REC_F4);
+                // |uv - pixel centre| over the pixels of the AABB's tiles (the rounding bound of cull_setup needs it)
+                const float px0 = (float)((xy & 0xffffu) * GSB_TILE), px1 = (float)(((xy & 0xffffu) + (wh & 0xffffu)) * GSB_TILE);
+                const float py0 = (float)((xy >> 16) * GSB_TILE), py1 = (float)(((xy >> 16) + (wh >> 16)) * GSB_TILE);
+                const float reach_x = fmaxf(fabsf(r0.x - px0), fabsf(px1 - r0.x)) + 1.0f;
+                const float reach_y = fmaxf(fabsf(r0.y - py0), fabsf(py1 - r0.y)) + 1.0f;
+                g = cull_setup(r0, q1.x, q1.y, reach_x, reach_y);
                 const int gx0 = (int)(xy & 0xffffu), gx1 = gx0 + (int)(wh & 0xffffu) - 1;
                 nt = 0;
                 for (uint32_t r = 0; r < (wh >> 16); r++) {

@@ -40,6 +40,11 @@ EXPORTED_SYMBOLS = [  # every symbol include/gs_b200.h declares
     "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers", "gsb_set_tile_cull",
     "gsb_reserve_instances", "gsb_render", "gsb_render_async", "gsb_get_stats", "gsb_debug_size",
     "gsb_debug_download", "gsb_sort_pairs", "gsb_sort_pairs32", "gsb_set_graph", "gsb_host_alloc", "gsb_host_free",
+    # frame sharding over several GPUs
+    "gsb_group_create", "gsb_group_destroy", "gsb_group_size", "gsb_group_context", "gsb_group_last_error",
+    "gsb_group_scene_upload", "gsb_group_render", "gsb_group_render_async",
+    "gsb_shard_unique_id", "gsb_shard_last_error", "gsb_create_sharded", "gsb_shard_rank", "gsb_shard_world", "gsb_shard_slice",
+    "gsb_shard_band", "gsb_scene_upload_sharded", "gsb_render_sharded", "gsb_render_sharded_async", "gsb_shard_frame",
 ]
 HOST_EXPORTED_SYMBOLS = [  # host/gs_b200_host.h
     "gsh_last_error", "gsh_initialize", "gsh_draw", "gsh_pan_translation", "gsh_movement", "gsh_cleanup",
@@ -112,6 +117,30 @@ lib.gsb_debug_size.restype = C.c_size_t
 lib.gsb_debug_download.argtypes = [_vp, C.c_int, _vp, C.c_size_t]
 lib.gsb_sort_pairs.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp]
 lib.gsb_sort_pairs32.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp]
+
+lib.gsb_group_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)]
+lib.gsb_group_destroy.argtypes = [_vp]
+lib.gsb_group_destroy.restype = None
+lib.gsb_group_size.argtypes = [_vp]
+lib.gsb_group_context.argtypes = [_vp, C.c_int]
+lib.gsb_group_context.restype = _vp
+lib.gsb_group_last_error.argtypes = [_vp]
+lib.gsb_group_last_error.restype = C.c_char_p
+lib.gsb_group_scene_upload.argtypes = [_vp, _vp, C.c_uint64, C.c_int]
+lib.gsb_group_render.argtypes = [_vp, C.POINTER(Uniforms), _vp, C.c_size_t, C.c_int, C.c_int]
+lib.gsb_group_render_async.argtypes = [_vp, C.POINTER(Uniforms), C.c_int]
+lib.gsb_shard_unique_id.argtypes = [_vp]
+lib.gsb_shard_last_error.restype = C.c_char_p
+lib.gsb_create_sharded.argtypes = [C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]
+lib.gsb_shard_rank.argtypes = [_vp]
+lib.gsb_shard_world.argtypes = [_vp]
+lib.gsb_shard_slice.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+lib.gsb_shard_band.argtypes = [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+lib.gsb_scene_upload_sharded.argtypes = [_vp, _vp, C.c_uint64, C.c_int]
+lib.gsb_render_sharded.argtypes = [_vp, C.POINTER(Uniforms), _vp, C.c_size_t, C.c_int, C.c_int, _vp]
+lib.gsb_render_sharded_async.argtypes = [_vp, C.POINTER(Uniforms), C.c_int, _vp]
+lib.gsb_shard_frame.argtypes = [_vp]
+lib.gsb_shard_frame.restype = _vp
 
 host.gsh_last_error.restype = C.c_char_p
 host.gsh_initialize.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
@@ -346,6 +375,104 @@ class Context:
     def sort_pairs32(self, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, m, key_bits=32, stream=None):
         self._ck(lib.gsb_sort_pairs32(self.h, keys_ptr, vals_ptr, keys_tmp_ptr, vals_tmp_ptr, m, key_bits,
                                       stream_ptr(stream)))
+
+
+# ---------------------------------------------------------------- one frame over several GPUs
+def shard_slice(n_total: int, rank: int, world: int):
+    """(first, count) of the Gaussians rank `rank` holds (gsb_shard_slice)."""
+    first, count = C.c_uint64(), C.c_uint64()
+    assert lib.gsb_shard_slice(n_total, rank, world, C.byref(first), C.byref(count)) == OK
+    return first.value, count.value
+
+
+def _frame_shape(u: Uniforms, fmt):
+    return (u.height, u.width, 4), (np.float32 if fmt == FORMAT_RGBA32F else np.uint8)
+
+
+class Group:
+    """gsb_group: one process drives `devices` (ids may repeat: several ranks on one GPU)."""
+
+    def __init__(self, devices):
+        devices = list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        h = _vp()
+        rc = lib.gsb_group_create(len(devices), arr, C.byref(h))
+        if rc != OK:
+            raise GsbError(rc, lib.gsb_shard_last_error().decode())
+        self.h = h
+        self.size = len(devices)
+
+    def close(self):
+        if self.h:
+            lib.gsb_group_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise GsbError(rc, lib.gsb_group_last_error(self.h).decode())
+
+    def context(self, rank) -> "Context":
+        return Context(handle=_vp(lib.gsb_group_context(self.h, rank)))
+
+    def upload(self, vertices: np.ndarray):
+        v = _f32(vertices).reshape(-1, 60)
+        self._ck(lib.gsb_group_scene_upload(self.h, v.ctypes.data, v.shape[0], MEM_HOST))
+
+    def render(self, u: Uniforms, fmt=FORMAT_RGBA32F) -> np.ndarray:
+        shape, dt = _frame_shape(u, fmt)
+        out = np.empty(shape, dt)
+        self._ck(lib.gsb_group_render(self.h, C.byref(u), out.ctypes.data, 0, MEM_HOST, fmt))
+        return out
+
+    def render_async(self, u: Uniforms, fmt=FORMAT_BGRA8):
+        self._ck(lib.gsb_group_render_async(self.h, C.byref(u), fmt))
+
+
+def shard_unique_id() -> bytes:
+    buf = (C.c_ubyte * 128)()
+    rc = lib.gsb_shard_unique_id(buf)
+    if rc != OK:
+        raise GsbError(rc, lib.gsb_shard_last_error().decode())
+    return bytes(buf)
+
+
+class ShardedContext(Context):
+    """gsb_create_sharded: this process is rank `rank` of `world` (one process per GPU)."""
+
+    def __init__(self, device, rank, world, unique_id: bytes):
+        h = _vp()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        rc = lib.gsb_create_sharded(device, rank, world, idbuf, C.byref(h))
+        if rc != OK:
+            raise GsbError(rc, lib.gsb_shard_last_error().decode() or lib.gsb_last_error(None).decode())
+        super().__init__(device, handle=h)
+        self._own = True
+        self.rank, self.world = rank, world
+
+    def upload_slice(self, slice_vertices: np.ndarray, n_total: int):
+        v = _f32(slice_vertices).reshape(-1, 60)
+        self._ck(lib.gsb_scene_upload_sharded(self.h, v.ctypes.data, n_total, MEM_HOST))
+
+    def render_sharded(self, u: Uniforms, fmt=FORMAT_RGBA32F, stream=None) -> np.ndarray:
+        shape, dt = _frame_shape(u, fmt)
+        out = np.empty(shape, dt)
+        self._ck(lib.gsb_render_sharded(self.h, C.byref(u), out.ctypes.data, 0, MEM_HOST, fmt, stream_ptr(stream)))
+        return out
+
+    def render_sharded_into(self, u: Uniforms, out_ptr, fmt, mem=MEM_DEVICE, stream=None):
+        self._ck(lib.gsb_render_sharded(self.h, C.byref(u), out_ptr, 0, mem, fmt, stream_ptr(stream)))
+
+    def render_sharded_async(self, u: Uniforms, fmt, stream=None):
+        self._ck(lib.gsb_render_sharded_async(self.h, C.byref(u), fmt, stream_ptr(stream)))
+
+    def frame_ptr(self) -> int:
+        return lib.gsb_shard_frame(self.h)
 
 
 # ---------------------------------------------------------------- the C++ host Renderer (vkgs_* style bridge)

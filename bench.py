@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 extra workload measured at --gpus 4 / 8")
     ap.add_argument("--tile-cull", type=int, default=1, help="gsb_set_tile_cull (exact instance culling; image bit-identical)")
     args = ap.parse_args()
 
@@ -257,47 +258,104 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    ctx = None
     if world > 1:
+        # torch.distributed only carries the 128-byte group id and the timing reductions; the frame's exchange (survivor
+        # routing + framebuffer) is the product's own: gsb_create_sharded / gsb_render_sharded (peer memory over NVLink)
         dist.init_process_group("nccl", device_id=dev)
-
-    vtx = make_scene(g, wl)
-    cams = cameras(g, wl)
-    W, H = wl["w"], wl["h"]
-    tiles_y = (H + 15) // 16
-    rb, re, rows_per = g.band_for_rank(H, rank, world)  # equal-height bands (all-gather needs equal counts)
-    band = (rb, re) if world > 1 else None
-
-    ctx = g.Context(local_rank)
+        box = [g.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx = g.ShardedContext(local_rank, rank, world, box[0])
+    else:
+        ctx = g.Context(local_rank)
     ctx.set_mode(g.MODE_EXACT if args.mode == "exact" else g.MODE_FAST)
     ctx.set_tile_cull(bool(args.tile_cull))
-    ctx.upload(vtx)
+
+    env = dict(g=g, torch=torch, dist=dist, dev=dev, rank=rank, world=world, local_rank=local_rank, ctx=ctx, args=args)
+    out = measure(env, wl_name, wl, args.steps, max(3, args.warmup), headline=True)
+    # BASELINE configs C4 / C5 are quoted on 4 / 8 GPUs: measured here as well and carried on the same JSON line (the headline
+    # workload stays the one `value` is quoted on, so the driver's 1 -> 8 scaling curve is over ONE workload)
+    extra_name = {4: "truck-standin", 8: "synthetic-50m"}.get(world) if not args.workload and not args.no_extra else None
+    if extra_name:
+        try:
+            ex = measure(env, extra_name, WORKLOADS[extra_name], min(args.steps, 50), 5, headline=False)
+            if rank == 0:
+                out["extra_workloads"] = [ex]
+        except Exception as exc:  # never lose the headline line over the extra workload
+            if rank == 0:
+                out["extra_workloads"] = [{"workload": extra_name, "error": repr(exc)}]
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _DevFrame:
+    """A device pointer dressed as a __cuda_array_interface__ object so torch can copy from it."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def measure(env, wl_name, wl, steps, warmup, headline):
+    """Uploads the workload and measures it on the context in `env` (single GPU: gsb_render*; N GPUs: gsb_render_sharded*).
+    Returns the JSON dict (rank 0) or None."""
+    g, torch, dist, dev, rank, world, ctx, args = (env[k] for k in ("g", "torch", "dist", "dev", "rank", "world", "ctx", "args"))
+    sharded = world > 1
+    W, H = wl["w"], wl["h"]
+    tiles_y = (H + 15) // 16
     fmt, bpp = g.FORMAT_BGRA8, 4
-    band_buf = torch.zeros((rows_per * 16, W, bpp), dtype=torch.uint8, device=dev)
-    full_buf = torch.zeros((world * rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) if world > 1 else band_buf
+    cams = cameras(g, wl)
+    t_load = time.perf_counter()
+    if sharded:
+        first, count = g.shard_slice(wl["n"], rank, world)  # the scene is sharded by Gaussian index: every rank builds its slice
+        vtx = make_scene(g, wl, first, count)
+        ctx.upload_slice(vtx, wl["n"])
+        del vtx
+    else:
+        vtx = make_scene(g, wl)
+        ctx.upload(vtx)
+    t_load = time.perf_counter() - t_load
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: NULL would mean the context's own stream
     torch.cuda.set_stream(stream)
+    dev_fb = [torch.zeros((H, W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)] if not sharded else None
 
-    # first frame sizes the instance arena (regrow path), then keep 25% headroom for the orbit
-    ctx.render_into(cams[0], band_buf.data_ptr(), fmt, rows=band, stream=stream, sync=True)
-    st0 = ctx.stats()
-    ctx.reserve(int(st0.num_instances * 1.3) + 65536)
-
-    def frame(i, sync):
-        if rb < re:
-            ctx.render_into(cams[i % NUM_CAMERAS], band_buf.data_ptr(), fmt, rows=band, stream=stream, sync=sync)
-        if world > 1:
-            dist.all_gather_into_tensor(full_buf.view(-1), band_buf.view(-1))
+    def frame(i, sync, k=0):
+        u = cams[i % NUM_CAMERAS]
+        if sharded:
+            if sync:
+                ctx.render_sharded_into(u, None, fmt, stream=stream)  # blocking, regrows collectively; frame stays in the window
+            else:
+                ctx.render_sharded_async(u, fmt, stream=stream)
+        else:
+            ctx.render_into(u, dev_fb[k].data_ptr(), fmt, stream=stream, sync=sync)
 
     def barrier():
-        if world > 1:
+        if sharded:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if sharded:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # first frames size the instance arena (regrow path), then keep headroom for the orbit
+    ctx.set_timers(True)
+    frame(0, sync=True)
+    peak_m = 0
+    for i in range(NUM_CAMERAS):
+        frame(i, sync=True)
+        peak_m = max(peak_m, ctx.stats().num_instances)
+    ctx.reserve(int(peak_m * 1.3) + 65536)
+    for i in range(warmup):
         frame(i, sync=True)
 
     # per-stage / per-kernel times (library cudaEvents), sampled on separate untimed frames
-    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc = {}, [], [], [], [], []
+    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc, visit_acc = {}, [], [], [], [], [], []
+    passes = 0
     for i in range(NUM_CAMERAS):
         frame(i, sync=True)
         s = ctx.stats()
@@ -309,34 +367,31 @@ def main():
         m_acc.append(s.num_instances)
         aabb_acc.append(s.num_instances_aabb)
         cons_acc.append(s.blend_consumed)
+        visit_acc.append(s.blend_warp_visits)
         vis_acc.append(s.num_visible)
         passes = s.sort_passes
         pass_acc.append(d["sort_pass_ms"])
     stage = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     pass_each = [float(x) for x in np.mean(np.array(pass_acc), axis=0)] if pass_acc and pass_acc[0] else []
-    M, NV, CONS = float(np.mean(m_acc)), float(np.mean(vis_acc)), float(np.mean(cons_acc))
+    M, NV, CONS, VISITS = float(np.mean(m_acc)), float(np.mean(vis_acc)), float(np.mean(cons_acc)), float(np.mean(visit_acc))
 
     # ---- value: K frames, device resident, one stream, CUDA events, max over ranks ----
     ctx.set_timers(False)  # from here on the camera-independent middle of the frame replays from a captured CUDA graph
     for i in range(NUM_CAMERAS):
         frame(i, sync=False)  # untimed: graph capture + instantiation happen here
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(env["local_rank"]) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         frame(i, sync=False)
     e1.record(stream)
     barrier()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / args.steps
-    ovf = ctx.stats()  # raises GSB_ERR_OVERFLOW if any async frame overflowed the arena (sticky flag)
-    del ovf
+    ms_step = reduce_max(e0.elapsed_time(e1)) / steps
+    ctx.stats()  # raises GSB_ERR_OVERFLOW if any async frame overflowed the arena (sticky flag)
 
     # ---- per-frame distribution (median / p95): the same frames again with an event after every frame ----
-    nd = min(args.steps, 200)
+    nd = min(steps, 200)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(nd + 1)]
     barrier()
     evs[0].record(stream)
@@ -346,155 +401,157 @@ def main():
     barrier()
     per_frame_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(nd)]
 
-    # ---- e2e: public C-ABI calls with HOST buffers: host UBO in every step, BGRA8 framebuffer copied device->host
-    # every step inside the timed region.  Two variants are timed; the headline is the pipelined one:
-    #   sync     : gsb_render(host UBO -> host frame), one blocking call per frame
-    #   pipelined: gsb_render_async into one of two device frames on the render stream + cudaMemcpyAsync of the
-    #              previous frame to pinned host memory on a copy stream (events order reuse); every frame still lands
-    #              in host memory inside the timed region, the copy just overlaps the next frame's kernels.
-    nrows = min(H, re * 16) - rb * 16 if rb < re else 0
-    host_fb = [torch.empty((max(nrows, 1), W, bpp), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    # ---- e2e: public C-ABI calls with HOST buffers: host UBO in every step, the whole BGRA8 frame in (rank 0's) pinned host
+    # memory every step, all inside the timed region.
+    #   sync     : one blocking call per frame: gsb_render(host UBO -> pinned host frame) -- the blend stores straight into the
+    #              host frame (N = 1); gsb_render_sharded(... -> host) = frame + one D2H copy of rank 0's whole frame (N > 1)
+    #   pipelined: enqueue-only render into one of two device frames + cudaMemcpyAsync of every frame to pinned host memory
+    #              on a copy stream (events order buffer reuse); the copy overlaps the next frame's kernels
+    host_fb = [torch.empty((H, W, bpp), dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        if nrows:
-            ctx._ck(g.lib.gsb_render(ctx.h, cams[i % NUM_CAMERAS], rb, re, host_fb[0].data_ptr(), 0, g.MEM_HOST, fmt, None))
+    for i in range(steps):
+        u = cams[i % NUM_CAMERAS]
+        if sharded:
+            ctx.render_sharded_into(u, host_fb[0].data_ptr() if rank == 0 else None, fmt, mem=g.MEM_HOST, stream=stream)
+        else:
+            ctx._ck(g.lib.gsb_render(ctx.h, u, 0, g.ALL_ROWS, host_fb[0].data_ptr(), 0, g.MEM_HOST, fmt, None))
     torch.cuda.synchronize()
-    e2e_sync_s = time.perf_counter() - t0
+    e2e_sync_fps = steps / reduce_max(time.perf_counter() - t0)
 
-    dev_fb = [torch.zeros((max(nrows, 1), W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)]
-    # N > 1: the bands are all-gathered on the device (as in `value`) and rank 0 copies the WHOLE frame to its host
-    # memory every step, so the end-to-end product is the same full framebuffer as at N = 1.
-    full_fb = [torch.zeros((world * rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
-    host_full = [torch.empty((world * rows_per * 16, W, bpp), dtype=torch.uint8).pin_memory() for _ in range(2)] if (world > 1 and rank == 0) else None
-    band_fb = [torch.zeros((rows_per * 16, W, bpp), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     copy_stream = torch.cuda.Stream(device=dev)
     rendered = [torch.cuda.Event() for _ in range(2)]
     copied = [torch.cuda.Event() for _ in range(2)]
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         k = i & 1
-        if world > 1:
-            if i >= 2:
-                stream.wait_event(copied[k])  # frame i-2 has left full_fb[k]
-            if rb < re:
-                ctx.render_into(cams[i % NUM_CAMERAS], band_fb[k].data_ptr(), fmt, rows=band, stream=stream, sync=False)
-            dist.all_gather_into_tensor(full_fb[k].view(-1), band_fb[k].view(-1))
-            rendered[k].record(stream)
-            if rank == 0:
-                copy_stream.wait_event(rendered[k])
-                with torch.cuda.stream(copy_stream):
-                    host_full[k].copy_(full_fb[k], non_blocking=True)
-            copied[k].record(copy_stream)
-        elif nrows:
-            if i >= 2:
-                stream.wait_event(copied[k])  # frame i-2 has left dev_fb[k]
-            ctx.render_into(cams[i % NUM_CAMERAS], dev_fb[k].data_ptr(), fmt, rows=(rb, re), stream=stream, sync=False)
-            rendered[k].record(stream)
+        if i >= 2:
+            stream.wait_event(copied[k])  # frame i - 2 has left the buffer frame i is about to overwrite
+        frame(i, sync=False, k=k)
+        rendered[k].record(stream)
+        if rank == 0:
+            src = torch.as_tensor(_DevFrame(ctx.frame_ptr(), (H, W, bpp)), device=dev) if sharded else dev_fb[k]
             copy_stream.wait_event(rendered[k])
             with torch.cuda.stream(copy_stream):
-                host_fb[k].copy_(dev_fb[k], non_blocking=True)
-                copied[k].record(copy_stream)
+                host_fb[k].copy_(src, non_blocking=True)
+        copied[k].record(copy_stream)
     torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_fps = args.steps / float(e2e_s.item())
-    e2e_sync_fps = args.steps / e2e_sync_s
-    ovf = ctx.stats()  # raises if an async frame overflowed the arena
-    del ovf
+    e2e_fps = steps / reduce_max(time.perf_counter() - t0)
+    ctx.stats()  # raises if an async frame overflowed the arena
     clocks = sampler.stop() if sampler else None
 
-    if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        nv = NV
-        # algorithmic bytes per launch (SURVEY 8d / DESIGN.md), one launch = one frame's worth of that kernel
-        T_tiles = ((W + 15) // 16) * tiles_y
-        kd = "sort_depth(hist+4 onesweep passes over N_v)"
-        alg = {
-            "k_project": wl["n"] * 40 + nv * 192 + nv * (48 + 8 + 8),  # scene read + SH of survivors + record/AABB/depth key+payload
-            kd: nv * (4 + 16 * 4 - 4),                                 # histogram read + 4 x (8 B read + 8 B written); the last pass writes no keys
-            "k_emit": nv * (4 + 8) + 8 * M,                            # sorted ids + AABBs in, (tile id, payload) out
-            "k_sort_hist": 4 * M,
-            # per launch, averaged over the passes: 8 B read + 8 B written per (tile id, payload) pair; the last pass
-            # writes payloads only (4 B) plus the tile ranges
-            "k_onesweep_pass": (16 * M * passes - 4 * M + 8 * T_tiles) / max(passes, 1),
-            "k_blend": CONS * (4 + 36) + (nrows if world == 1 else H) * W * bpp,
-        }
-        dur = {"k_project": stage["preprocess_ms"], kd: stage["sort_depth_ms"], "k_emit": stage["preprocess_sort_ms"],
-               "k_sort_hist": stage["sort_hist_ms"], "k_onesweep_pass": stage["sort_pass_ms"],
-               "k_blend": stage["render_ms"]}
-        share = dict(dur)
-        share["k_onesweep_pass"] = stage["sort_pass_ms"] * passes
-        kern = {k: {"ms_per_launch": dur[k], "launches_per_step": passes if k == "k_onesweep_pass" else (5 if k == kd else 1),
-                    "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (dur[k] * 1e-3) / 1e9 if dur[k] > 0 else None,
-                    "share_of_step": share[k] / stage["frame_ms"] if stage["frame_ms"] > 0 else None} for k in alg}
-        dom = max(share, key=share.get)
-        traffic = None
-        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-            tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-            traffic = tj["dram_bytes_per_launch"].get(dom)
-        except Exception:
-            pass
-        roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["achieved_gbs"] / peak if kern[dom]["achieved_gbs"] else None, "traffic": traffic,
-                "peak_source": peak_src,
-                "note": "k_blend is FP32/SFU-issue bound (SURVEY 8d): its HBM fraction is reported as required, pair-evals/s beside it"}
-        out = {
-            "metric": "frames/sec", "value": 1000.0 / ms_step, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {**bench_config(wl_name, wl),
-                       "instances_M": M, "instances_aabb": float(np.mean(aabb_acc)), "tile_cull": bool(args.tile_cull), "visible": NV, "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8",
-                       "l2": "inputs (1.3 GB scene + 0.4 GB keys) larger than the 126 MB L2; no flush",
-                       "parallelism": f"tile-row bands x{world}" if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 160,
-                    "d2h_bytes_per_step": (int(world * rows_per * 16 * W * bpp) if world > 1 else int(nrows * W * bpp)) + 64,
-                    "api": ("gsb_render_async(host UBO) per band + NCCL all-gather on the device + cudaMemcpyAsync of every whole BGRA8 frame to rank 0's pinned host memory, double buffered"
-                            if world > 1 else "gsb_render_async(host UBO) + cudaMemcpyAsync of every BGRA8 frame to pinned host memory, double buffered"),
-                    "sync_value": e2e_sync_fps, "sync_api": "gsb_render(host UBO -> host BGRA8), one blocking call per frame"},
-            # k_frame_init, k_project, hist + 4 passes (depth), k_emit, hist + P passes (tile; the last one also writes the
-            # tile ranges), k_blend -- the sorts and the emission are launched through one captured CUDA graph per frame
-            "gpu_launches": int((10 + passes) * args.steps),
-            "clocks": clocks,
-            "roofline": roof,
-            "kernels": kern,
-            "stage_ms": stage,
-            "sort_pass_ms_each": pass_each,
-            "sort_keys_per_s": M / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
-            "blend_pair_evals_per_s": CONS * 256 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
-        }
-        try:  # M for every timed camera, median / p95 of the per-camera frame time (library timers)
-            fm = [float(x) for x in stage_acc.get("frame_ms", [])]
-            out["per_camera"] = {"frame_ms": fm, "instances": [int(x) for x in m_acc],
-                                 "frame_ms_median": float(np.median(fm)) if fm else None,
-                                 "frame_ms_p95": float(np.percentile(fm, 95)) if fm else None}
-            out["frame_ms_distribution"] = {"frames": len(per_frame_ms), "median": float(np.median(per_frame_ms)),
-                                            "p95": float(np.percentile(per_frame_ms, 95)), "max": float(np.max(per_frame_ms)),
-                                            "how": "cudaEvent after every frame of the device-resident loop (this rank)"}
-        except Exception as exc:  # reporting only: never lose the bench line over it
-            out["per_camera"] = {"error": str(exc)}
-        if world == 1 and not args.no_cpu_baseline:
-            sys.path.insert(0, str(ROOT / "oracle"))
-            import oracle as o
-            cores = use_all_cores(o)
-            cov = o.cov3d(vtx)
-            r = cpu_oracle_frame(o, vtx, cov, cams[0])  # calibration / warm-up
-            if r["t_frame_s"] <= 10.0:  # whole frames, nothing extrapolated (garden: ~2 s each)
-                rs = [cpu_oracle_frame(o, vtx, cov, cams[k % NUM_CAMERAS]) for k in range(max(1, min(8, int(20.0 / r["t_frame_s"]))))]
-                fps = float(np.mean([x["fps"] for x in rs]))
-                sample = f"{len(rs)} WHOLE frames of the CPU oracle ({np.mean([x['t_frame_s'] for x in rs]):.2f} s each), nothing extrapolated"
-            else:
-                r = cpu_oracle_sample(wl, vtx, cams[0], 20.0, cov)
-                fps = r["fps"]
-                sample = (f"all {wl['n']} Gaussians preprocessed, tile rows {r['rows']} of {r['tiles_y']} sorted+blended "
-                          f"({r['sample_wall_s']:.1f}s wall), EXTRAPOLATED by rows_total/rows_band")
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(out))
-    ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    per_rank = None
+    if sharded:  # band imbalance: every rank's instance count and device frame time (library timers) for one pose
+        ctx.set_timers(True)
+        frame(0, sync=True)
+        frame(0, sync=True)
+        s = ctx.stats()
+        mine = {"rank": rank, "visible": int(s.num_visible), "instances": int(s.num_instances), "frame_ms": float(s.frame_ms),
+                "project_exchange_ms": float(s.preprocess_ms), "blend_ms": float(s.render_ms)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        ctx.set_timers(False)
+    if rank != 0:
+        return None
+
+    peak, peak_src = measured_peak_gbs()
+    nv = NV
+    n_local = wl["n"] / world
+    # algorithmic bytes per launch (SURVEY 8d / DESIGN.md), one launch = one frame's worth of that kernel ON THIS RANK
+    T_tiles = ((W + 15) // 16) * tiles_y
+    kd = "sort_depth(hist+4 onesweep passes over N_v)"
+    alg = {
+        "k_project": n_local * 40 + (nv * 192 + nv * (64 + 8)) * (1.0 if not sharded else 1.0),  # scene read + SH of survivors + 64-B record, depth key + payload
+        kd: nv * (4 + 16 * 4 - 4),                                 # histogram read + 4 x (8 B read + 8 B written); the last pass writes no keys
+        "k_emit": nv * (4 + 32) + 8 * M,                           # sorted ids + one 32-B record sector per survivor in, (tile id, payload) out
+        "k_sort_hist": 4 * M,
+        # per launch, averaged over the passes: 8 B read + 8 B written per (tile id, payload) pair; the last pass
+        # writes payloads only (4 B) plus the tile ranges
+        "k_onesweep_pass": (16 * M * passes - 4 * M + 8 * T_tiles) / max(passes, 1),
+        "k_blend": CONS * (4 + 36) + H * W * bpp / world * (world if sharded else 1),
+    }
+    dur = {"k_project": stage["preprocess_ms"], kd: stage["sort_depth_ms"], "k_emit": stage["preprocess_sort_ms"],
+           "k_sort_hist": stage["sort_hist_ms"], "k_onesweep_pass": stage["sort_pass_ms"],
+           "k_blend": stage["render_ms"]}
+    share = dict(dur)
+    share["k_onesweep_pass"] = stage["sort_pass_ms"] * passes
+    kern = {k: {"ms_per_launch": dur[k], "launches_per_step": passes if k == "k_onesweep_pass" else (5 if k == kd else 1),
+                "alg_bytes_per_launch": alg[k], "achieved_gbs": alg[k] / (dur[k] * 1e-3) / 1e9 if dur[k] > 0 else None,
+                "share_of_step": share[k] / stage["frame_ms"] if stage["frame_ms"] > 0 else None} for k in alg}
+    dom = max(share, key=share.get)
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (headline workload, N = 1)
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        traffic = tj["dram_bytes_per_launch"].get(dom) if (headline and not sharded) else None
+    except Exception:
+        pass
+    roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kern[dom]["achieved_gbs"] / peak if kern[dom]["achieved_gbs"] else None, "traffic": traffic,
+            "peak_source": peak_src,
+            "note": "k_blend is FP32-issue bound, not HBM bound (SURVEY 8d): its HBM fraction is reported as required; "
+                    "blend_warp_visits_per_s x the SASS instructions per visit (profiles/) is its issue-slot utilisation"}
+    out = {
+        "metric": "frames/sec", "value": 1000.0 / ms_step, "unit": "frames/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {**bench_config(wl_name, wl),
+                   "instances_M": M, "instances_aabb": float(np.mean(aabb_acc)), "tile_cull": bool(args.tile_cull), "visible": NV,
+                   "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8", "scene_load_s": t_load,
+                   "l2": "inputs (scene + sort keys, > 1 GB) larger than the 126 MB L2; 8 camera poses alternate; no flush",
+                   "parallelism": (f"scene sharded by Gaussian index x{world}, frame by tile-row bands x{world}; survivors and framebuffer "
+                                   f"exchanged by stores into peer memory (NVLink), no collective in the frame" if sharded else "single GPU")},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": int(H * W * bpp) + 64,
+                "api": ("gsb_render_sharded_async(host UBO) on every rank + cudaMemcpyAsync of every whole BGRA8 frame from rank 0's copy to its pinned host memory, double buffered"
+                        if sharded else "gsb_render_async(host UBO) + cudaMemcpyAsync of every BGRA8 frame to pinned host memory, double buffered"),
+                "sync_value": e2e_sync_fps,
+                "sync_api": ("gsb_render_sharded(host UBO -> rank 0's pinned host BGRA8 frame), one blocking collective call per frame" if sharded
+                             else "gsb_render(host UBO -> pinned host BGRA8 frame: the blend stores straight into host memory), one blocking call per frame")},
+        # k_frame_init, k_project, hist + 4 passes (depth), k_emit, hist + P passes (tile; the last one also writes the tile
+        # ranges), k_blend -- the sorts and the emission are launched through one captured CUDA graph per frame; sharded
+        # frames add k_route, k_shard_gather and 3 signal + 3 wait one-warp kernels
+        "gpu_launches": int((10 + passes + (8 if sharded else 0)) * steps),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernels": kern,
+        "stage_ms": stage,
+        "sort_pass_ms_each": pass_each,
+        "sort_keys_per_s": M / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
+        # evaluated work, not the algorithmic pair count: one visit = one (warp, record) iteration of the blend's inner loop = 64
+        # pixel x Gaussian pairs evaluated (k_blend2: 2 pixels per lane)
+        "blend_warp_visits_per_s": VISITS / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
+        "blend_pairs_evaluated_per_s": VISITS * 64 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
+    }
+    if sharded:
+        out["per_rank"] = per_rank
+        out["stage_ms_note"] = "stage times, instance counts and rooflines are rank 0's (its band, its slice); per_rank has every rank's frame"
+    try:  # M for every timed camera, median / p95 of the per-camera frame time (library timers)
+        fm = [float(x) for x in stage_acc.get("frame_ms", [])]
+        out["per_camera"] = {"frame_ms": fm, "instances": [int(x) for x in m_acc],
+                             "frame_ms_median": float(np.median(fm)) if fm else None,
+                             "frame_ms_p95": float(np.percentile(fm, 95)) if fm else None}
+        out["frame_ms_distribution"] = {"frames": len(per_frame_ms), "median": float(np.median(per_frame_ms)),
+                                        "p95": float(np.percentile(per_frame_ms, 95)), "max": float(np.max(per_frame_ms)),
+                                        "how": "cudaEvent after every frame of the device-resident loop (this rank)"}
+    except Exception as exc:  # reporting only: never lose the bench line over it
+        out["per_camera"] = {"error": str(exc)}
+    if headline and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import oracle as o
+        cores = use_all_cores(o)
+        cov = o.cov3d(vtx)
+        r = cpu_oracle_frame(o, vtx, cov, cams[0])  # calibration / warm-up
+        if r["t_frame_s"] <= 10.0:  # whole frames, nothing extrapolated (garden: ~2-3 s each)
+            rs = [cpu_oracle_frame(o, vtx, cov, cams[k % NUM_CAMERAS]) for k in range(max(1, min(8, int(20.0 / r["t_frame_s"]))))]
+            fps = float(np.mean([x["fps"] for x in rs]))
+            sample = f"{len(rs)} WHOLE frames of the CPU oracle ({np.mean([x['t_frame_s'] for x in rs]):.2f} s each), nothing extrapolated"
+        else:
+            r = cpu_oracle_sample(wl, vtx, cams[0], 20.0, cov)
+            fps = r["fps"]
+            sample = (f"all {wl['n']} Gaussians preprocessed, tile rows {r['rows']} of {r['tiles_y']} sorted+blended "
+                      f"({r['sample_wall_s']:.1f}s wall), EXTRAPOLATED by rows_total/rows_band")
+        out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    return out
 
 
 if __name__ == "__main__":

@@ -201,6 +201,51 @@ int gsb_sort_pairs(gsb_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_
 int gsb_sort_pairs32(gsb_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
                      uint64_t m, uint32_t key_bits, void *stream);
 
+/* ---- one frame over several GPUs of an NVSwitch domain (SURVEY 8b `gs_create_sharded`, 8e) ----
+ * No reference counterpart (the reference is single-GPU).  The scene is sharded by Gaussian index (rank r holds and
+ * projects slice r), the frame by tile rows (rank d sorts and blends band d); survivors travel from their slice's rank
+ * to their band's rank(s) and the blended bands to every rank's whole-frame buffer by stores into peer-mapped memory
+ * (NVLink), ordered by mailbox words -- no collective call in the frame.  Every rank ends the frame holding the whole
+ * framebuffer, bit-identical to a single-GPU gsb_render of the same scene and camera.
+ *
+ * (a) one process drives all GPUs.  `devices` = ndev CUDA device ids (NULL: 0 .. ndev-1); an id may repeat (several
+ *     ranks on one GPU -- how the single-GPU tests cover the protocol).  vertices = all n GSScene::Vertex records. */
+typedef struct gsb_group gsb_group;
+int gsb_group_create(int ndev, const int *devices, gsb_group **out);
+void gsb_group_destroy(gsb_group *g);
+int gsb_group_size(const gsb_group *g);
+gsb_ctx *gsb_group_context(gsb_group *g, int rank); /* per-rank context: gsb_set_mode / _tile_cull / _timers, gsb_get_stats */
+const char *gsb_group_last_error(const gsb_group *g);
+int gsb_group_scene_upload(gsb_group *g, const float *vertices, uint64_t n, gsb_memory mem);
+/* Renders the frame on all GPUs and waits; grows instance arenas and re-renders on overflow like gsb_render.  `out` (may be
+ * NULL) receives the whole frame from rank 0's copy; gsb_shard_frame(gsb_group_context(g, r)) is rank r's device copy. */
+int gsb_group_render(gsb_group *g, const gsb_uniforms *ubo, void *out, size_t row_pitch_bytes, gsb_memory out_mem, gsb_format fmt);
+int gsb_group_render_async(gsb_group *g, const gsb_uniforms *ubo, gsb_format fmt); /* enqueue only, never synchronises */
+
+/* (b) one process per GPU (torchrun / MPI).  Rank 0 calls gsb_shard_unique_id and the host program distributes the 128
+ *     bytes by any means; NCCL (dlopen'ed libnccl.so.2, used only here) bootstraps the group and carries the cudaIpc handles
+ *     of the exchange windows.  GSB_SHARD_GATHER=nccl reassembles the framebuffer with one in-place ncclAllGather instead
+ *     of the blend's peer stores (the baseline the fused path is measured against). */
+typedef struct gsb_shard_id { unsigned char bytes[128]; } gsb_shard_id;
+int gsb_shard_unique_id(gsb_shard_id *out);
+const char *gsb_shard_last_error(void); /* text of the last gsb_shard_unique_id / gsb_create_sharded / gsb_group_create error */
+int gsb_create_sharded(int device, int rank, int world, const gsb_shard_id *id, gsb_ctx **out); /* gsb_destroy frees it */
+int gsb_shard_rank(const gsb_ctx *ctx);
+int gsb_shard_world(const gsb_ctx *ctx);
+/* Slice of rank `rank`: Gaussians [first, first + count) with S = ceil(n_total / world), first = rank * S. */
+int gsb_shard_slice(uint64_t n_total, int rank, int world, uint64_t *first, uint64_t *count);
+/* Tile rows [begin, end) of the frame this rank blends at image height `height` (equal-height bands). */
+int gsb_shard_band(const gsb_ctx *ctx, uint32_t height, uint32_t *row_begin, uint32_t *row_end);
+/* slice_vertices = this rank's slice only (gsb_shard_slice), n_total = size of the whole scene. */
+int gsb_scene_upload_sharded(gsb_ctx *ctx, const float *slice_vertices, uint64_t n_total, gsb_memory mem);
+/* Collective: every rank calls it with the same ubo / fmt.  Waits for the frame; `out` (may be NULL) receives this rank's
+ * copy of the WHOLE frame.  The first call at a new frame size (re)allocates and re-exchanges the windows. */
+int gsb_render_sharded(gsb_ctx *ctx, const gsb_uniforms *ubo, void *out, size_t row_pitch_bytes, gsb_memory out_mem,
+                       gsb_format fmt, void *stream);
+int gsb_render_sharded_async(gsb_ctx *ctx, const gsb_uniforms *ubo, gsb_format fmt, void *stream);
+/* This rank's device copy of the last whole frame (tight pitch); valid until the second-next render call. */
+const void *gsb_shard_frame(const gsb_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif

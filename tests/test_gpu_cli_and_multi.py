@@ -1,6 +1,7 @@
 """(1) The C++ headless viewer (apps/viewer/main.cpp's flags without a window) end to end on a small PLY.
-(2) Two-GPU tile-row sharding with a real NCCL all-gather (skipped on a one-GPU box): the gathered frame must be
-bit-identical to the single-GPU frame."""
+(2) Frame sharding over real GPUs (skipped on a one-GPU box; tests/test_gpu_shard.py covers the protocol on one GPU): one
+process per GPU through gsb_create_sharded / gsb_render_sharded, and one process driving all GPUs through gsb_group_*; the
+frame every rank ends up with must be bit-identical to the single-GPU frame."""
 import json
 import os
 import subprocess
@@ -55,37 +56,64 @@ def test_headless_viewer_cli(gs, oracle, tmp_path):
 
 
 WORKER = r'''
+# one process per GPU through the product's own ABI: gsb_create_sharded (NCCL bootstrap + cudaIpc windows), scene sharded by
+# Gaussian index, gsb_render_sharded (peer-memory routing + peer-store blend); torch.distributed only carries the 128-byte id
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.join(os.environ["GS_ROOT"], "3dgs.cpp_b200", "python")); sys.path.insert(0, os.path.join(os.environ["GS_ROOT"], "tests"))
 import gs_b200 as g, scenes
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(rank); dev = torch.device("cuda", rank)
-dist.init_process_group("nccl", device_id=dev)
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")
+box = [g.shard_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(box, src=0)
+ctx = g.ShardedContext(rank, rank, world, box[0])
 _, vtx, _ = scenes.c1()
-u = scenes.camera("odd_size")
-ctx = g.Context(rank); ctx.upload(vtx)
-rb, re, rows_per = g.band_for_rank(u.height, rank, world)
-band = torch.zeros((rows_per * 16, u.width, 4), dtype=torch.float32, device=dev)
-full = torch.zeros((world * rows_per * 16, u.width, 4), dtype=torch.float32, device=dev)
-s = torch.cuda.Stream(device=dev); torch.cuda.set_stream(s)
-if rb < re: ctx.render_into(u, band.data_ptr(), g.FORMAT_RGBA32F, rows=(rb, re), stream=s, sync=True)
-dist.all_gather_into_tensor(full.view(-1), band.view(-1))
-torch.cuda.synchronize()
+first, count = g.shard_slice(vtx.shape[0], rank, world)
+ctx.upload_slice(vtx[first:first + count], vtx.shape[0])
+ok = True
+single = g.Context(rank); single.upload(vtx)
+for cam in ("odd_size", "c1", "inside", "c1"):
+    u = scenes.camera(cam)
+    for fmt in (g.FORMAT_RGBA32F, g.FORMAT_BGRA8):
+        got = ctx.render_sharded(u, fmt)                 # every rank receives the whole frame
+        ok = ok and np.array_equal(got, single.render(u, fmt))
+flags = [None] * world
+dist.all_gather_object(flags, bool(ok))
 if rank == 0:
-    single = ctx.render(u, g.FORMAT_RGBA32F)
-    ok = np.array_equal(full[:u.height].cpu().numpy(), single)
-    print("MULTI_OK" if ok else "MULTI_MISMATCH")
+    print("MULTI_OK" if all(flags) else f"MULTI_MISMATCH {flags}")
+ctx.close(); single.close()
 dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_sharded_frame_equals_single_gpu(gs, tmp_path):
+def _gpus():
     torch = pytest.importorskip("torch")
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("gather", ["peer", "nccl"])
+def test_two_gpu_sharded_frame_equals_single_gpu(gs, tmp_path, gather):
+    if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, GS_ROOT=str(ROOT))
+    env = dict(os.environ, GS_ROOT=str(ROOT), GSB_SHARD_GATHER=gather)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_in_process_group_over_all_gpus(gs, ctx):
+    n = _gpus()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    _, vtx, _ = scenes.c1()
+    ctx.upload(vtx)
+    grp = gs.Group(list(range(min(n, 8))))
+    try:
+        grp.upload(vtx)
+        for cam in ("c1", "odd_size", "wide"):
+            u = scenes.camera(cam)
+            assert np.array_equal(grp.render(u, gs.FORMAT_RGBA32F), ctx.render(u, gs.FORMAT_RGBA32F)), cam
+    finally:
+        grp.close()
