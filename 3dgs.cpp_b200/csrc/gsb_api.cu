@@ -264,6 +264,21 @@ int launch_middle_graph(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) 
     return GSB_OK;
 }
 
+// Tile ranges for a W x H frame.  cudaMalloc / cudaFree may wait for every device that has this one peer-mapped, so a
+// group that drives several GPUs from one host thread calls this for every rank BEFORE enqueuing any rank's frame (a rank
+// already spinning in k_shard_wait for a peer whose enqueue is stuck behind an allocation would only leave by timeout).
+int ensure_ranges(gsb_ctx* ctx, uint32_t W, uint32_t H) {
+    const uint32_t T = ((W + GSB_TILE - 1) / GSB_TILE) * ((H + GSB_TILE - 1) / GSB_TILE);
+    if (T > ctx->ranges_tiles) {
+        dev_free(ctx->ranges);
+        ctx->ranges_tiles = 0;
+        ctx->alloc_gen++;
+        CK(dev_alloc(&ctx->ranges, T));
+        ctx->ranges_tiles = T;
+    }
+    return GSB_OK;
+}
+
 int plan_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, cudaStream_t stream, FramePlan* out) {
     FramePlan fp{};
     fp.W = ubo->width;
@@ -273,11 +288,9 @@ int plan_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
     fp.T = fp.tiles_x * fp.tiles_y;
     fp.rb = rb;
     fp.re = re;
-    if (fp.T > ctx->ranges_tiles) {
-        dev_free(ctx->ranges);
-        ctx->alloc_gen++;
-        CK(dev_alloc(&ctx->ranges, fp.T));
-        ctx->ranges_tiles = fp.T;
+    {
+        int rc = ensure_ranges(ctx, fp.W, fp.H);
+        if (rc != GSB_OK) return rc;
     }
     const uint32_t n = (uint32_t)ctx->n;
     fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : n), quantise_hint(n));
@@ -749,6 +762,7 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
     out->num_instances_aabb = c->candidates_total;
     out->blend_consumed = c->blend_consumed;
     out->blend_warp_visits = c->blend_walked;
+    out->blend_pixel_hits = c->blend_hits;
     out->instance_capacity = ctx->capacity;
     out->sort_passes = ctx->last_passes;
     out->sort_depth_passes = ctx->last_depth_passes;

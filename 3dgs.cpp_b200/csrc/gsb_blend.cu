@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     __shared__ StagedRec2 s_rec[B2_BATCH];
     __shared__ uint8_t s_mask[B2_BATCH];
     __shared__ uint16_t s_list[B2_WARPS][B2_BATCH];  // per warp: shared-window addresses of the records it must visit
-    __shared__ uint32_t s_used, s_walked;
+    __shared__ uint32_t s_used, s_walked, s_hits;
     static_assert(sizeof(StagedRec2) * B2_BATCH < 65536, "u16 list entries hold shared-window addresses");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,13 +425,14 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     if (tid == 0) {
         s_used = 0;
         s_walked = 0;
+        s_hits = 0;
     }
     __syncthreads();
 
     // transmittance (0 = finished or outside the image) and colour a/b/c of pixel 0/1
     float T0 = in0 ? 1.0f : 0.0f, T1 = in1 ? 1.0f : 0.0f, ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f, cc0 = 0.f, cc1 = 0.f;
 #define B2_DONE (T0 == 0.0f && T1 == 0.0f)
-    uint32_t used = 0, walked = 0;
+    uint32_t used = 0, walked = 0, hits = 0;
     const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);
     const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
 
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
                     if (STATS) {
                         const uint32_t u = base_off + __float_as_uint(idxf) + 1u;
                         used = ((in0k && !ok0 && T0 != 0.0f) || (in1k && !ok1 && T1 != 0.0f)) ? max(used, u) : used;
+                        hits += (in0k && T0 != 0.0f ? 1u : 0u) + (in1k && T1 != 0.0f ? 1u : 0u);
                     }
 #if GSB_BLEND2_PRED
                     // predicated scalar accumulates (FMA pipe) instead of packed adds + selects (the half-rate ALU pipe is
@@ -577,6 +579,9 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     if (STATS) {
         if (in0 || in1) atomicMax(&s_used, used);
         if (lane == 0 && walked) atomicAdd(&s_walked, walked);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(FULL, hits, o);
+        if (lane == 0 && hits) atomicAdd(&s_hits, hits);
     }
     // Destinations: the caller's buffer, or -- frame sharding -- the whole-frame buffer of EVERY rank (peer memory over
     // NVLink; posted stores, so the framebuffer exchange rides under the blend instead of following it as a collective).
@@ -624,6 +629,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
         if (tid == 0) {
             if (s_used) atomicAdd(&P.ctl->blend_consumed, (unsigned long long)s_used);
             if (s_walked) atomicAdd(&P.ctl->blend_walked, (unsigned long long)s_walked);
+            if (s_hits) atomicAdd(&P.ctl->blend_hits, (unsigned long long)s_hits);
         }
     }
 }

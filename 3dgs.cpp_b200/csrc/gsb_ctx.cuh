@@ -131,6 +131,7 @@ uint32_t bits_for(uint32_t count);
 uint32_t quantise_hint(uint64_t hint);
 size_t bytes_per_pixel(int fmt);
 int wait_frame(gsb_ctx* ctx);
+int ensure_ranges(gsb_ctx* ctx, uint32_t W, uint32_t H);
 // fills the size-derived fields of a plan, (re)allocates the tile ranges and handles the look-back epoch wrap
 int plan_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, cudaStream_t stream, FramePlan* out);
 int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool events);

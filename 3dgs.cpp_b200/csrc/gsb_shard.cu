@@ -445,137 +445,177 @@ PeerWords words_of(ShardState* sh, size_t field_offset, int index_is_rank, int p
 
 constexpr long long WAIT_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s at 1.9 GHz: a dead peer becomes an error, not a hung GPU
 
-// Enqueue one sharded frame on `stream`.  Collective: every rank enqueues the same frame; never blocks the host.
-int enqueue_sharded(gsb_ctx* ctx, const gsb_uniforms* ubo, int fmt, cudaStream_t stream) {
+// One sharded frame is enqueued in four phases; a phase ends where the stream would next WAIT for the other ranks:
+//   1  frame start, signal `started`, k_project over the local slice
+//   2  wait `started`, k_route (stores into peer memory), signal `routed`
+//   3  wait `routed`, gather, depth sort / emission / tile sort, blend (peer stores), signal `framed`
+//   4  wait `framed`, mailbox + stats copy, completion event
+// A process that drives ONE rank enqueues 1-4 back to back.  A group that drives every rank from one host thread enqueues
+// phase k of EVERY rank before phase k + 1 of any: each wait is then enqueued after all the signals it depends on, so a
+// host-side call that blocks until another device drains (first-use module loading, cudaMalloc / cudaFree with peer
+// mappings) can never sit between a spinning wait and the signal that would release it.  (Measured on 2 x B200:
+// enqueuing rank 0's whole frame first left it spinning in k_shard_wait until the 3 s timeout while rank 1's first
+// launches were stuck behind it.)
+struct ShardFrame {
+    gsb_uniforms ubo;
+    int fmt = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t f = 0, R = 0, tiles_y = 0, rb = 0, re = 0;
+    int par = 0;
+    FramePlan fp{};
+};
+
+int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
     ShardState* sh = ctx->shard;
     const int G = sh->world, r = sh->rank;
-    const uint32_t W = ubo->width, H = ubo->height;
-    const uint32_t tiles_y = (H + GSB_TILE - 1) / GSB_TILE;
-    const uint32_t R = (tiles_y + G - 1) / G;
-    const uint32_t rb = std::min(tiles_y, (uint32_t)r * R), re = std::min(tiles_y, rb + R);
-    const uint32_t f = ++sh->frame;
-    const int par = (int)(f & 1u);
-    sh->last_parity = (uint32_t)par;
+    cudaStream_t stream = F.stream;
     Mailbox* mb = sh->mailbox(r);
-
-    // the dense destination-side arrays and the exchange buffers of this parity take the place of the plain context's
-    // survivor arrays for the middle of the frame and the blend
-    FramePlan fp{};
-    const uint64_t n_local = ctx->n;
-    int rc = plan_frame(ctx, ubo, rb, re, stream, &fp);
-    if (rc != GSB_OK) return rc;
-    fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : sh->cap), quantise_hint(sh->cap));
-    const uint32_t chunks_local = (uint32_t)((n_local + 255) / 256), chunks_cap = (uint32_t)((sh->cap + 255) / 256);
-
-    CK(launch_frame_init(ctx->ctl, ctx->project_status, sh->emit_status_d, std::max(std::max(chunks_local, chunks_cap), 1u), ctx->ranges,
-                         fp.T, stream, sh->route_status, std::max(chunks_local, 1u) * GSB_MAX_SHARDS));
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
-    // S1: I have entered frame f (my buffers of parity f & 1 -- last used by frame f - 2 -- may be overwritten)
-    k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, started), 1, 0), f, G, PeerWords{}, nullptr, 0);
-
-    // ---- k_project over the local slice, whole frame (no band clip): source-side compaction ----
-    ProjectParams pp{};
-    pp.pos_op = ctx->pos_op;
-    pp.cov_a = ctx->cov_a;
-    pp.cov_b = ctx->cov_b;
-    pp.sh = ctx->sh;
-    pp.n = (uint32_t)n_local;
-    pp.index_base = (uint32_t)((uint64_t)r * sh->slice);
-    pp.ubo = *ubo;
-    pp.tile_row_begin = 0;
-    pp.tile_row_end = tiles_y;
-    pp.recs = ctx->recs;
-    pp.dkeys = ctx->dkeys[0];
-    pp.dvals = ctx->dvals[0];
-    pp.status = ctx->project_status;
-    pp.ctl = ctx->ctl;
-    CK(launch_project(pp, false, stream));
-
-    // ---- exchange: wait until every rank has entered the frame, deliver, announce, wait for everyone's delivery ----
-    k_shard_wait<<<1, 32, 0, stream>>>(mb->started, f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
-    RouteParams rp{};
-    rp.d_nv = &ctx->ctl->num_visible;
-    rp.recs = ctx->recs;
-    rp.dkeys = ctx->dkeys[0];
-    rp.status = sh->route_status;
-    rp.ctl = ctx->ctl;
-    rp.world = G;
-    rp.band_rows = std::max(R, 1u);
-    for (int d = 0; d < G; d++) {
-        rp.dst_recs[d] = sh->recs_x(d, par) + (size_t)r * sh->slice * GSB_REC_F4;
-        rp.dst_dkeys[d] = sh->dkeys_x(d, par) + (size_t)r * sh->slice;
-    }
-    {
-        const uint32_t hint = sh->nv_local_hint ? sh->nv_local_hint : (uint32_t)n_local;
-        uint32_t blocks = std::min<uint32_t>((quantise_hint(hint) + ROUTE_THREADS - 1) / ROUTE_THREADS, (uint32_t)ctx->num_sms * 4u);
-        k_route<<<std::max(blocks, 1u), ROUTE_THREADS, 0, stream>>>(rp);
-    }
-    k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, routed), 1, 0), f, G,
-                                         words_of(sh, offsetof(Mailbox, count), 1, par * GSB_MAX_SHARDS), ctx->ctl->route_total, 1);
-    k_shard_wait<<<1, 32, 0, stream>>>(mb->routed, f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
-    if (ctx->timers) CK(cudaEventRecord(ctx->ev[1], stream));  // "preprocess" = projection + exchange
-
-    GatherParams gp{};
-    gp.counts = mb->count[par];
-    gp.dkeys_x = sh->dkeys_x(r, par);
-    gp.slice = (uint32_t)sh->slice;
-    gp.world = G;
-    gp.dkeys = sh->dkeys_d[0];
-    gp.dvals = sh->dvals_d[0];
-    gp.ctl = ctx->ctl;
-    k_shard_gather<<<std::min<uint32_t>((fp.nv_q + 255) / 256, (uint32_t)ctx->num_sms * 8u), 256, 0, stream>>>(gp);
-    CK(cudaGetLastError());
-
-    // ---- the middle of the frame and the blend run on the destination-side arrays ----
-    struct Swap {
-        gsb_ctx* c;
-        float4* recs;
-        uint32_t* dk[2];
-        uint32_t* dv[2];
-        unsigned long long* es;
-        uint32_t tag;
-        ~Swap() {
-            c->recs = recs;
-            c->dkeys[0] = dk[0];
-            c->dkeys[1] = dk[1];
-            c->dvals[0] = dv[0];
-            c->dvals[1] = dv[1];
-            c->emit_status = es;
-            c->middle_tag = tag;
-        }
-    } swap{ctx, ctx->recs, {ctx->dkeys[0], ctx->dkeys[1]}, {ctx->dvals[0], ctx->dvals[1]}, ctx->emit_status, ctx->middle_tag};
-    ctx->recs = sh->recs_x(r, par);
-    ctx->dkeys[0] = sh->dkeys_d[0];
-    ctx->dkeys[1] = sh->dkeys_d[1];
-    ctx->dvals[0] = sh->dvals_d[0];
-    ctx->dvals[1] = sh->dvals_d[1];
-    ctx->emit_status = sh->emit_status_d;
-    ctx->middle_tag = 1u + (uint32_t)par;
-    if (ctx->use_graph && !ctx->timers && !ctx->debug) rc = launch_middle_graph(ctx, fp, stream);
-    else rc = enqueue_middle(ctx, fp, stream, ctx->timers);
-    if (rc != GSB_OK) return rc;
-
-    const size_t pitch = (size_t)W * bytes_per_pixel(fmt);
-    void* frames[GSB_MAX_SHARDS];
-    for (int p = 0; p < G; p++) frames[p] = sh->frame_x(p, par);
-    if (rb < re) {
-        if (sh->gather_nccl) rc = enqueue_blend(ctx, fp, rb, re, nullptr, pitch, fmt, stream, &frames[r], 1);
-        else rc = enqueue_blend(ctx, fp, rb, re, nullptr, pitch, fmt, stream, frames, G);
+    if (phase == 1) {
+        const gsb_uniforms* ubo = &F.ubo;
+        const uint32_t H = ubo->height;
+        F.tiles_y = (H + GSB_TILE - 1) / GSB_TILE;
+        F.R = (F.tiles_y + G - 1) / G;
+        F.rb = std::min(F.tiles_y, (uint32_t)r * F.R);
+        F.re = std::min(F.tiles_y, F.rb + F.R);
+        F.f = ++sh->frame;
+        F.par = (int)(F.f & 1u);
+        sh->last_parity = (uint32_t)F.par;
+        // the dense destination-side arrays and the exchange buffers of this parity take the place of the plain context's
+        // survivor arrays for the middle of the frame and the blend
+        const uint64_t n_local = ctx->n;
+        int rc = plan_frame(ctx, ubo, F.rb, F.re, stream, &F.fp);
         if (rc != GSB_OK) return rc;
+        F.fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : sh->cap), quantise_hint(sh->cap));
+        const uint32_t chunks_local = (uint32_t)((n_local + 255) / 256), chunks_cap = (uint32_t)((sh->cap + 255) / 256);
+        CK(launch_frame_init(ctx->ctl, ctx->project_status, sh->emit_status_d, std::max(std::max(chunks_local, chunks_cap), 1u), ctx->ranges,
+                             F.fp.T, stream, sh->route_status, std::max(chunks_local, 1u) * GSB_MAX_SHARDS));
+        if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
+        // S1: I have entered frame f (my buffers of parity f & 1 -- last used by frame f - 2 -- may be overwritten)
+        k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, started), 1, 0), F.f, G, PeerWords{}, nullptr, 0);
+        // ---- k_project over the local slice, whole frame (no band clip): source-side compaction ----
+        ProjectParams pp{};
+        pp.pos_op = ctx->pos_op;
+        pp.cov_a = ctx->cov_a;
+        pp.cov_b = ctx->cov_b;
+        pp.sh = ctx->sh;
+        pp.n = (uint32_t)n_local;
+        pp.index_base = (uint32_t)((uint64_t)r * sh->slice);
+        pp.ubo = *ubo;
+        pp.tile_row_begin = 0;
+        pp.tile_row_end = F.tiles_y;
+        pp.recs = ctx->recs;
+        pp.dkeys = ctx->dkeys[0];
+        pp.dvals = ctx->dvals[0];
+        pp.status = ctx->project_status;
+        pp.ctl = ctx->ctl;
+        CK(launch_project(pp, false, stream));
+        return GSB_OK;
     }
-    if (sh->gather_nccl && sh->comm) {  // the baseline: one in-place all-gather of the equal-height bands
-        const size_t band_bytes = (size_t)R * GSB_TILE * pitch;
-        unsigned char* fb = static_cast<unsigned char*>(frames[r]);
-        ncclResult_t nr = sh->nccl.AllGather(fb + (size_t)r * band_bytes, fb, band_bytes, ncclChar, sh->comm, stream);
-        if (nr != ncclSuccess) return fail(ctx, GSB_ERR_CUDA, (std::string("ncclAllGather: ") + sh->nccl.GetErrorString(nr)).c_str());
+    if (phase == 2) {
+        // ---- exchange: wait until every rank has entered the frame, deliver, announce ----
+        k_shard_wait<<<1, 32, 0, stream>>>(mb->started, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
+        RouteParams rp{};
+        rp.d_nv = &ctx->ctl->num_visible;
+        rp.recs = ctx->recs;
+        rp.dkeys = ctx->dkeys[0];
+        rp.status = sh->route_status;
+        rp.ctl = ctx->ctl;
+        rp.world = G;
+        rp.band_rows = std::max(F.R, 1u);
+        for (int d = 0; d < G; d++) {
+            rp.dst_recs[d] = sh->recs_x(d, F.par) + (size_t)r * sh->slice * GSB_REC_F4;
+            rp.dst_dkeys[d] = sh->dkeys_x(d, F.par) + (size_t)r * sh->slice;
+        }
+        const uint32_t hint = sh->nv_local_hint ? sh->nv_local_hint : (uint32_t)ctx->n;
+        const uint32_t blocks = std::min<uint32_t>((quantise_hint(hint) + ROUTE_THREADS - 1) / ROUTE_THREADS, (uint32_t)ctx->num_sms * 4u);
+        k_route<<<std::max(blocks, 1u), ROUTE_THREADS, 0, stream>>>(rp);
+        k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, routed), 1, 0), F.f, G,
+                                             words_of(sh, offsetof(Mailbox, count), 1, F.par * GSB_MAX_SHARDS), ctx->ctl->route_total, 1);
+        CK(cudaGetLastError());
+        return GSB_OK;
     }
-    // S3: my band (and my overflow flag) has landed everywhere; wait for everyone's
-    k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, framed), 1, 0), f, G,
-                                         words_of(sh, offsetof(Mailbox, overflow), 1, par * GSB_MAX_SHARDS), &ctx->ctl->overflow, 0);
-    k_shard_wait<<<1, 32, 0, stream>>>(mb->framed, f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
+    if (phase == 3) {
+        k_shard_wait<<<1, 32, 0, stream>>>(mb->routed, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
+        if (ctx->timers) CK(cudaEventRecord(ctx->ev[1], stream));  // "preprocess" = projection + exchange
+        GatherParams gp{};
+        gp.counts = mb->count[F.par];
+        gp.dkeys_x = sh->dkeys_x(r, F.par);
+        gp.slice = (uint32_t)sh->slice;
+        gp.world = G;
+        gp.dkeys = sh->dkeys_d[0];
+        gp.dvals = sh->dvals_d[0];
+        gp.ctl = ctx->ctl;
+        k_shard_gather<<<std::min<uint32_t>((F.fp.nv_q + 255) / 256, (uint32_t)ctx->num_sms * 8u), 256, 0, stream>>>(gp);
+        CK(cudaGetLastError());
+
+        // ---- the middle of the frame and the blend run on the destination-side arrays ----
+        struct Swap {
+            gsb_ctx* c;
+            float4* recs;
+            uint32_t* dk[2];
+            uint32_t* dv[2];
+            unsigned long long* es;
+            uint32_t tag;
+            ~Swap() {
+                c->recs = recs;
+                c->dkeys[0] = dk[0];
+                c->dkeys[1] = dk[1];
+                c->dvals[0] = dv[0];
+                c->dvals[1] = dv[1];
+                c->emit_status = es;
+                c->middle_tag = tag;
+            }
+        } swap{ctx, ctx->recs, {ctx->dkeys[0], ctx->dkeys[1]}, {ctx->dvals[0], ctx->dvals[1]}, ctx->emit_status, ctx->middle_tag};
+        ctx->recs = sh->recs_x(r, F.par);
+        ctx->dkeys[0] = sh->dkeys_d[0];
+        ctx->dkeys[1] = sh->dkeys_d[1];
+        ctx->dvals[0] = sh->dvals_d[0];
+        ctx->dvals[1] = sh->dvals_d[1];
+        ctx->emit_status = sh->emit_status_d;
+        ctx->middle_tag = 1u + (uint32_t)F.par;
+        int rc;
+        if (ctx->use_graph && !ctx->timers && !ctx->debug) rc = launch_middle_graph(ctx, F.fp, stream);
+        else rc = enqueue_middle(ctx, F.fp, stream, ctx->timers);
+        if (rc != GSB_OK) return rc;
+
+        const size_t pitch = (size_t)F.ubo.width * bytes_per_pixel(F.fmt);
+        void* frames[GSB_MAX_SHARDS];
+        for (int p = 0; p < G; p++) frames[p] = sh->frame_x(p, F.par);
+        if (F.rb < F.re) {
+            if (sh->gather_nccl) rc = enqueue_blend(ctx, F.fp, F.rb, F.re, nullptr, pitch, F.fmt, stream, &frames[r], 1);
+            else rc = enqueue_blend(ctx, F.fp, F.rb, F.re, nullptr, pitch, F.fmt, stream, frames, G);
+            if (rc != GSB_OK) return rc;
+        }
+        if (sh->gather_nccl && sh->comm) {  // the baseline: one in-place all-gather of the equal-height bands
+            const size_t band_bytes = (size_t)F.R * GSB_TILE * pitch;
+            unsigned char* fb = static_cast<unsigned char*>(frames[r]);
+            ncclResult_t nr = sh->nccl.AllGather(fb + (size_t)r * band_bytes, fb, band_bytes, ncclChar, sh->comm, stream);
+            if (nr != ncclSuccess) return fail(ctx, GSB_ERR_CUDA, (std::string("ncclAllGather: ") + sh->nccl.GetErrorString(nr)).c_str());
+        }
+        // S3: my band (and my overflow flag) has landed everywhere
+        k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, framed), 1, 0), F.f, G,
+                                             words_of(sh, offsetof(Mailbox, overflow), 1, F.par * GSB_MAX_SHARDS), &ctx->ctl->overflow, 0);
+        CK(cudaGetLastError());
+        return GSB_OK;
+    }
+    // phase 4: wait for everyone's band
+    k_shard_wait<<<1, 32, 0, stream>>>(mb->framed, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sh->mailbox_host, mb, sizeof(Mailbox), cudaMemcpyDeviceToHost, stream));
-    return enqueue_tail(ctx, fp, stream);
+    return enqueue_tail(ctx, F.fp, stream);
+}
+
+// Enqueue one sharded frame of ONE rank on `stream`.  Collective: every rank enqueues the same frame; never blocks the host.
+int enqueue_sharded(gsb_ctx* ctx, const gsb_uniforms* ubo, int fmt, cudaStream_t stream) {
+    ShardFrame F;
+    F.ubo = *ubo;
+    F.fmt = fmt;
+    F.stream = stream;
+    for (int phase = 1; phase <= 4; phase++) {
+        int rc = enqueue_sharded_phase(ctx, F, phase);
+        if (rc != GSB_OK) return rc;
+    }
+    return GSB_OK;
 }
 
 // after wait_frame(): peer timeout? any rank's arena overflowed (every rank sees the same flags -> same decision)?
@@ -938,16 +978,32 @@ static int group_enqueue(gsb_group* g, const gsb_uniforms* ubo, int fmt) {
         int rc = ensure_windows_group(g);
         if (rc != GSB_OK) return rc;
     }
-    for (gsb_ctx* c : g->ctx) {  // one host thread enqueues every rank's frame; the ranks meet on the device
+    for (gsb_ctx* c : g->ctx) {  // every allocation of every rank first (see ensure_ranges)
+        cudaSetDevice(c->device);
+        int rc = ensure_ranges(c, ubo->width, ubo->height);
+        if (rc != GSB_OK) return group_fail(g, rc, c->err);
+    }
+    std::vector<ShardFrame> F(g->ctx.size());
+    for (size_t i = 0; i < g->ctx.size(); i++) {
+        gsb_ctx* c = g->ctx[i];
         cudaSetDevice(c->device);
         if (c->frame_pending && cudaEventQuery(c->ev_done) == cudaSuccess) {
             c->frame_pending = false;
             c->m_hint = c->ctl_host->num_instances;
             c->nv_hint = c->ctl_host->num_visible;
         }
-        int rc = enqueue_sharded(c, ubo, fmt, c->stream);
-        if (rc != GSB_OK) return group_fail(g, rc, c->err);
+        F[i].ubo = *ubo;
+        F[i].fmt = fmt;
+        F[i].stream = c->stream;
     }
+    // one host thread enqueues every rank's frame, phase by phase (see enqueue_sharded_phase); the ranks meet on the device
+    for (int phase = 1; phase <= 4; phase++)
+        for (size_t i = 0; i < g->ctx.size(); i++) {
+            gsb_ctx* c = g->ctx[i];
+            cudaSetDevice(c->device);
+            int rc = enqueue_sharded_phase(c, F[i], phase);
+            if (rc != GSB_OK) return group_fail(g, rc, c->err);
+        }
     return GSB_OK;
 }
 

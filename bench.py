@@ -354,7 +354,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         frame(i, sync=True)
 
     # per-stage / per-kernel times (library cudaEvents), sampled on separate untimed frames
-    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc, visit_acc = {}, [], [], [], [], [], []
+    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc, visit_acc, hit_acc = {}, [], [], [], [], [], [], []
     passes = 0
     for i in range(NUM_CAMERAS):
         frame(i, sync=True)
@@ -368,6 +368,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         aabb_acc.append(s.num_instances_aabb)
         cons_acc.append(s.blend_consumed)
         visit_acc.append(s.blend_warp_visits)
+        hit_acc.append(s.blend_pixel_hits)
         vis_acc.append(s.num_visible)
         passes = s.sort_passes
         pass_acc.append(d["sort_pass_ms"])
@@ -521,6 +522,9 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         # pixel x Gaussian pairs evaluated (k_blend2: 2 pixels per lane)
         "blend_warp_visits_per_s": VISITS / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
         "blend_pairs_evaluated_per_s": VISITS * 64 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
+        # of the evaluated pairs, the fraction that passes render.comp:68-80 (the rest is SIMT lanes riding along)
+        "blend_lane_utilisation": float(np.mean(hit_acc)) / (VISITS * 64) if VISITS > 0 else None,
+        "blend_records_consumed": CONS, "blend_warp_visits": VISITS,
     }
     if sharded:
         out["per_rank"] = per_rank

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 2
+#define GSB_ABI_VERSION 3
 
 typedef struct gsb_ctx gsb_ctx;
 
@@ -121,6 +121,8 @@ typedef struct gsb_stats {
     uint32_t pad_;
     uint64_t blend_warp_visits; /* (warp, record) visits of the blend's inner loop = evaluated pixel-pair x Gaussian work / 64
                                    (each visit evaluates 64 pixels); counted only while timers or debug are on */
+    uint64_t blend_pixel_hits;  /* (pixel, Gaussian) pairs of those visits that passed render.comp:68-80 (power <= 0 and
+                                   alpha >= 1/255): hits / (64 * visits) = SIMT lane utilisation of the blend's walk */
 } gsb_stats;
 
 /* ---- lifetime: replaces Renderer::initializeVulkan + create*Pipeline (Renderer.cpp:119-155,166-364) ---- */

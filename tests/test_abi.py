@@ -29,10 +29,10 @@ def test_host_bridge_exports_every_declared_symbol(gs):
 
 
 def test_abi_version_and_struct_sizes(gs):
-    assert gs.lib.gsb_abi_version() == 2
+    assert gs.lib.gsb_abi_version() == 3
     assert C.sizeof(gs.Uniforms) == 160  # Renderer::UniformBuffer, std140
     assert gs.ATTR_DTYPE.itemsize == 64  # VertexAttribute
-    assert C.sizeof(gs.Stats) == 6 * 8 + 2 * 4 + 7 * 4 + 3 * 4 + 8 * 4 + 2 * 4 + 8
+    assert C.sizeof(gs.Stats) == 6 * 8 + 2 * 4 + 7 * 4 + 3 * 4 + 8 * 4 + 2 * 4 + 8 + 8
 
 
 def test_no_cpu_fallback_without_device(gs):
