@@ -792,6 +792,12 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
         out->render_ms = ms;
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]));
         out->frame_ms = ms;
+        if (ctx->shard) {
+            CK(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[7]));
+            out->shard_blend_ms = ms;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[6]));
+            out->shard_wait_ms = ms;
+        }
     }
     if (c->overflow || c->overflow_sticky) {
         // sticky: set by ANY frame since the last report (pipelined gsb_render_async frames overwrite the per-frame flag)

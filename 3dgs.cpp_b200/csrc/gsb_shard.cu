@@ -592,6 +592,7 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
             ncclResult_t nr = sh->nccl.AllGather(fb + (size_t)r * band_bytes, fb, band_bytes, ncclChar, sh->comm, stream);
             if (nr != ncclSuccess) return fail(ctx, GSB_ERR_CUDA, (std::string("ncclAllGather: ") + sh->nccl.GetErrorString(nr)).c_str());
         }
+        if (ctx->timers) CK(cudaEventRecord(ctx->ev[7], stream));  // end of this rank's own blend (gsb_stats::shard_blend_ms)
         // S3: my band (and my overflow flag) has landed everywhere
         k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, framed), 1, 0), F.f, G,
                                              words_of(sh, offsetof(Mailbox, overflow), 1, F.par * GSB_MAX_SHARDS), &ctx->ctl->overflow, 0);

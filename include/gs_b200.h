@@ -123,6 +123,8 @@ typedef struct gsb_stats {
                                    (each visit evaluates 64 pixels); counted only while timers or debug are on */
     uint64_t blend_pixel_hits;  /* (pixel, Gaussian) pairs of those visits that passed render.comp:68-80 (power <= 0 and
                                    alpha >= 1/255): hits / (64 * visits) = SIMT lane utilisation of the blend's walk */
+    float shard_blend_ms;       /* frame sharding only: this rank's blend kernel alone (render_ms also holds the wait below) */
+    float shard_wait_ms;        /* frame sharding only: from the end of this rank's blend until every rank's band has landed */
 } gsb_stats;
 
 /* ---- lifetime: replaces Renderer::initializeVulkan + create*Pipeline (Renderer.cpp:119-155,166-364) ---- */
