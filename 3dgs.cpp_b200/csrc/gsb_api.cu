@@ -111,9 +111,9 @@ int wait_frame(gsb_ctx* ctx) {
     return GSB_OK;
 }
 
-static __global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project_status, unsigned long long* __restrict__ emit_status,
-                                    uint32_t chunks, uint2* __restrict__ ranges, uint32_t num_tiles, uint32_t* __restrict__ extra_words,
-                                    uint32_t num_extra_words) {
+static __global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project_status, uint32_t project_chunks,
+                                    unsigned long long* __restrict__ emit_status, uint32_t emit_chunks, uint2* __restrict__ ranges,
+                                    uint32_t num_tiles, uint32_t* __restrict__ extra_words, uint32_t num_extra_words) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     uint32_t* w = reinterpret_cast<uint32_t*>(ctl);
     for (uint32_t k = i; k < sizeof(Control) / 4; k += stride) {
@@ -121,19 +121,21 @@ static __global__ void k_frame_init(Control* ctl, uint32_t* __restrict__ project
         if (k == offsetof(Control, epoch) / 4) w[k] += 16u;          // fresh look-back tags for this frame's two sorts
         else w[k] = 0u;
     }
-    for (uint32_t k = i; k < chunks; k += stride) {
-        project_status[k] = 0u;
-        emit_status[k] = 0ull;
-    }
+    // the two look-back arrays have different lengths on a sharded context (local slice vs. the band's whole survivor list)
+    for (uint32_t k = i; k < project_chunks; k += stride) project_status[k] = 0u;
+    for (uint32_t k = i; k < emit_chunks; k += stride) emit_status[k] = 0ull;
     for (uint32_t k = i; k < num_tiles; k += stride) ranges[k] = make_uint2(0xffffffffu, 0xffffffffu);  // tile_boundary's fillBuffer (Renderer.cpp:633)
     for (uint32_t k = i; k < num_extra_words; k += stride) extra_words[k] = 0u;  // frame sharding: k_route's look-back words
 }
 
-cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, unsigned long long* emit_status, uint32_t chunks,
-                              uint2* ranges, uint32_t num_tiles, cudaStream_t s, uint32_t* extra_words, uint32_t num_extra_words) {
-    const uint32_t work = std::max<uint32_t>(std::max(std::max(chunks, num_tiles), num_extra_words), (uint32_t)(sizeof(Control) / 4));
+cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, uint32_t project_chunks, unsigned long long* emit_status,
+                              uint32_t emit_chunks, uint2* ranges, uint32_t num_tiles, cudaStream_t s, uint32_t* extra_words,
+                              uint32_t num_extra_words) {
+    const uint32_t work = std::max<uint32_t>(std::max(std::max(std::max(project_chunks, emit_chunks), num_tiles), num_extra_words),
+                                             (uint32_t)(sizeof(Control) / 4));
     const uint32_t blocks = std::min<uint32_t>((work + 255) / 256, 148u * 4u);
-    k_frame_init<<<blocks, 256, 0, s>>>(ctl, project_status, emit_status, chunks, ranges, num_tiles, extra_words, num_extra_words);
+    k_frame_init<<<blocks, 256, 0, s>>>(ctl, project_status, project_chunks, emit_status, emit_chunks, ranges, num_tiles, extra_words,
+                                        num_extra_words);
     return cudaGetLastError();
 }
 
@@ -315,7 +317,7 @@ static int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uin
     const uint32_t n = (uint32_t)ctx->n;
     const uint32_t chunks = (n + 255) / 256;
     const bool timers = ctx->timers;
-    CK(launch_frame_init(ctx->ctl, ctx->project_status, ctx->emit_status, std::max(chunks, 1u), ctx->ranges, fp.T, stream));
+    CK(launch_frame_init(ctx->ctl, ctx->project_status, std::max(chunks, 1u), ctx->emit_status, std::max(chunks, 1u), ctx->ranges, fp.T, stream));
     if (timers) CK(cudaEventRecord(ctx->ev[0], stream));
 
     // ---- k_project: preprocess.comp + survivor compaction ----

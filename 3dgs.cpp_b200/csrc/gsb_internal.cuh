@@ -118,8 +118,8 @@ uint32_t sort_tile_items();
 
 // One kernel instead of four memsets: zeroes the control block (keeping overflow_sticky) and the look-back words of
 // k_project / k_emit, and fills the tile ranges with (0xFFFFFFFF, 0xFFFFFFFF) = empty.
-cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, unsigned long long* emit_status, uint32_t chunks,
-                              uint2* ranges, uint32_t num_tiles, cudaStream_t s, uint32_t* extra_words = nullptr,
+cudaError_t launch_frame_init(Control* ctl, uint32_t* project_status, uint32_t project_chunks, unsigned long long* emit_status,
+                              uint32_t emit_chunks, uint2* ranges, uint32_t num_tiles, cudaStream_t s, uint32_t* extra_words = nullptr,
                               uint32_t num_extra_words = 0);
 cudaError_t sort_prepare();  // one-time function attributes (dynamic shared memory opt-in) of the Onesweep kernels
 cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaStream_t s);

@@ -487,7 +487,8 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
         if (rc != GSB_OK) return rc;
         F.fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : sh->cap), quantise_hint(sh->cap));
         const uint32_t chunks_local = (uint32_t)((n_local + 255) / 256), chunks_cap = (uint32_t)((sh->cap + 255) / 256);
-        CK(launch_frame_init(ctx->ctl, ctx->project_status, sh->emit_status_d, std::max(std::max(chunks_local, chunks_cap), 1u), ctx->ranges,
+        // project_status covers the local slice, emit_status_d the band's survivor list (up to `cap` slots)
+        CK(launch_frame_init(ctx->ctl, ctx->project_status, std::max(chunks_local, 1u), sh->emit_status_d, std::max(chunks_cap, 1u), ctx->ranges,
                              F.fp.T, stream, sh->route_status, std::max(chunks_local, 1u) * GSB_MAX_SHARDS));
         if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
         // S1: I have entered frame f (my buffers of parity f & 1 -- last used by frame f - 2 -- may be overwritten)

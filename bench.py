@@ -450,7 +450,8 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         s = ctx.stats()
         mine = {"rank": rank, "visible": int(s.num_visible), "instances": int(s.num_instances), "frame_ms": float(s.frame_ms),
                 "project_exchange_ms": float(s.preprocess_ms), "blend_ms": float(s.shard_blend_ms), "band_wait_ms": float(s.shard_wait_ms),
-                "depth_sort_ms": float(s.sort_depth_ms), "emit_ms": float(s.preprocess_sort_ms), "tile_sort_ms": float(s.sort_tile_ms)}
+                "depth_sort_ms": float(s.sort_depth_ms), "emit_ms": float(s.preprocess_sort_ms), "tile_sort_ms": float(s.sort_tile_ms),
+                "blend_consumed": int(s.blend_consumed), "blend_warp_visits": int(s.blend_warp_visits)}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
         ctx.set_timers(False)

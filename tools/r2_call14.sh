@@ -1,0 +1,9 @@
+N=${1:-4}
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_gpu_shard.py tests/test_gpu_cli_and_multi.py -m gpu -q -x ) 2>&1 | tail -3
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_shard.py -m gpu -q -x -k "bit_identical and 3" > gpurun_out/r2_san_shard.log 2>&1; echo "sanitizer rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid" gpurun_out/r2_san_shard.log | head -5
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 100 --warmup 10 > gpurun_out/r2m_g${N}.json 2> gpurun_out/r2m_g${N}.err || tail -c 1500 gpurun_out/r2m_g${N}.err
+python -c "
+import json;d=json.loads(open('gpurun_out/r2m_g${N}.json').read().strip().splitlines()[-1]);print('gpus',d['n_gpus'],'fps',round(d['value'],1),'e2e',round(d['e2e']['value'],1),'sync',round(d['e2e']['sync_value'],1),{k:round(v,3) for k,v in d['stage_ms'].items()})
+for r in d.get('per_rank'): print({k:(round(v,3) if isinstance(v,float) else v) for k,v in r.items()})
+for e in d.get('extra_workloads',[]): print(e.get('config',{}).get('workload'), e.get('value'), e.get('e2e',{}).get('value'), e.get('error'))"
