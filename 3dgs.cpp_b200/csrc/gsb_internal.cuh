@@ -73,6 +73,14 @@ struct ProjectParams {
     // debug outputs (may be null)
     uint32_t* dbg_tiles;  // N
     uint4* dbg_aabb;      // N
+    // frame sharding (route_world > 0): instead of compacting into recs / dkeys, every survivor is delivered -- its 64-B record
+    // with the tile AABB clipped to the band, and its depth key -- into the exchange buffers of each rank whose band (band_rows
+    // tile rows per rank) its AABB touches; route_dst_* point at THIS source's region inside rank d's buffers (peer memory)
+    int route_world;
+    uint32_t band_rows;
+    uint32_t* route_status;  // [chunks][GSB_MAX_SHARDS] look-back words, one column per destination
+    float4* route_dst_recs[GSB_MAX_SHARDS];
+    uint32_t* route_dst_dkeys[GSB_MAX_SHARDS];
 };
 
 struct EmitParams {

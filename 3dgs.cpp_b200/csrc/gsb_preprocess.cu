@@ -125,11 +125,18 @@ __device__ __forceinline__ void compute_sh(const float4* __restrict__ sh4, float
 #ifndef GSB_PROJECT_MIN_BLOCKS
 #define GSB_PROJECT_MIN_BLOCKS 6  // <= 42 registers: 6 CTAs (48 warps) per SM hide the SH gather latency (measured 0.264 ms vs 0.30 at 5 CTAs, 0.42 at 80 registers)
 #endif
-template <bool DEBUG>
+// ROUTED (frame sharding, gsb_shard.cu): the single stream compaction becomes one compaction per destination band -- G
+// simultaneous decoupled look-back scans over G-wide status vectors, warp d walking column d -- and the record goes straight
+// from registers into the exchange buffer of every rank whose band the AABB touches (stores into peer-mapped memory over
+// NVLink).  Slots are deterministic (Gaussian-index order inside this source's region), so every band's survivor list is
+// ordered exactly like the single-GPU compaction and the band's pixels are bit-identical.
+template <bool DEBUG, bool ROUTED>
 __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project(const __grid_constant__ ProjectParams P) {
     __shared__ uint32_t s_chunk;
     __shared__ uint32_t s_wsurv[PRE_THREADS / 32];
     __shared__ uint32_t s_base_surv;
+    __shared__ uint32_t s_rcnt[ROUTED ? PRE_THREADS / 32 : 1][GSB_MAX_SHARDS];  // per warp, per destination: touching lanes
+    __shared__ uint32_t s_rbase[GSB_MAX_SHARDS];                                // chunk total, then exclusive base
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_chunk = atomicAdd(&P.ctl->project_ticket, 1u);
@@ -228,6 +235,93 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
         }
     }
 
+    if constexpr (ROUTED) {
+        const int G = P.route_world;
+        // ---- per destination band: does the AABB touch it, rank among the warp's touching lanes (5 bits each, packed) ----
+        uint32_t touch = 0;
+        unsigned long long ranks = 0ull;
+#pragma unroll
+        for (int d = 0; d < GSB_MAX_SHARDS; d++) {
+            if (d < G) {
+                const int b0 = d * (int)P.band_rows, b1 = b0 + (int)P.band_rows;
+                const bool t = surv && max(by0, b0) < min(by1, b1);
+                const unsigned bits = __ballot_sync(FULL, t);
+                if (t) touch |= 1u << d;
+                ranks |= (unsigned long long)__popc(bits & ((1u << lane) - 1u)) << (5 * d);
+                if (lane == 0) s_rcnt[warp][d] = __popc(bits);
+            }
+        }
+        __syncthreads();
+        if (tid < G) {  // thread d: exclusive scan over the warps, chunk total, publish the aggregate as early as possible
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < PRE_THREADS / 32; w++) {
+                const uint32_t c = s_rcnt[w][tid];
+                s_rcnt[w][tid] = run;
+                run += c;
+            }
+            s_rbase[tid] = run;
+            st_vol(P.route_status + (size_t)chunk * GSB_MAX_SHARDS + tid, (chunk == 0 ? S1_PREFIX : S1_AGG) | run);
+        }
+        // ---- SH colour of survivors (overlaps the look-back of other chunks) ----
+        float colr = 0.f, colg = 0.f, colb = 0.f;
+        if (surv) compute_sh(reinterpret_cast<const float4*>(P.sh) + (size_t)i * 12, px, py, pz, U.camera_position, colr, colg, colb);
+        __syncthreads();
+        // ---- decoupled look-back: warp d walks column d of the status vectors, 32 predecessors per step ----
+        if (warp < G) {
+            const int d = warp;
+            const uint32_t total = s_rbase[d];
+            uint32_t ex = 0;
+            if (chunk != 0) {
+                int look = (int)chunk - 1;
+                while (true) {
+                    const int idx = look - lane;
+                    uint32_t st = S1_PREFIX;  // virtual predecessor of chunk 0
+                    if (idx >= 0) {
+                        st = ld_vol(P.route_status + (size_t)idx * GSB_MAX_SHARDS + d);
+                        while ((st & S1_FLAGS) == 0) st = ld_vol(P.route_status + (size_t)idx * GSB_MAX_SHARDS + d);
+                    }
+                    const unsigned pm = __ballot_sync(FULL, (st & S1_FLAGS) == S1_PREFIX);
+                    const int first = pm ? (__ffs(pm) - 1) : 32;
+                    uint32_t cs = (lane <= first) ? (st & S1_COUNT) : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(FULL, cs, o);
+                    ex += cs;
+                    if (pm) break;
+                    look -= 32;
+                }
+                if (lane == 0) st_vol(P.route_status + (size_t)chunk * GSB_MAX_SHARDS + d, S1_PREFIX | (ex + total));
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_rbase[d] = ex;
+                if (chunk == num_chunks - 1) P.ctl->route_total[d] = ex + total;
+            }
+        }
+        __syncthreads();
+        // ---- deliver: one 64-B record + depth key per touched band, straight from registers ----
+        if (touch) {
+            const float4 q0 = make_float4(uvx, uvy, conx, cony);
+            const float4 q2 = make_float4(colr, colg, colb, depth);
+            const float4 q3 = make_float4(radii, __uint_as_float(P.index_base + i), 0.f, 0.f);
+            const uint32_t dk = __float_as_uint(depth);
+#pragma unroll
+            for (int d = 0; d < GSB_MAX_SHARDS; d++) {
+                if (d < G && ((touch >> d) & 1u)) {
+                    const uint32_t pos = s_rbase[d] + s_rcnt[warp][d] + (uint32_t)((ranks >> (5 * d)) & 31ull);
+                    const int b0 = d * (int)P.band_rows, b1 = b0 + (int)P.band_rows;
+                    const int cy0 = max(by0, b0), cy1 = min(by1, b1);  // the band clip k_project applies on one GPU
+                    float4* dst = P.route_dst_recs[d] + (size_t)pos * GSB_REC_F4;
+                    dst[0] = q0;
+                    dst[1] = make_float4(conz, opac, __uint_as_float((uint32_t)bx0 | ((uint32_t)cy0 << 16)),
+                                         __uint_as_float((uint32_t)(bx1 - bx0) | ((uint32_t)(cy1 - cy0) << 16)));
+                    dst[2] = q2;
+                    dst[3] = q3;
+                    P.route_dst_dkeys[d][pos] = dk;
+                }
+            }
+        }
+    } else {
     // ---- block scan of the survivor flags ----
     const unsigned surv_mask = __ballot_sync(FULL, surv);
     const uint32_t surv_rank_w = __popc(surv_mask & ((1u << lane) - 1u));
@@ -288,6 +382,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
         rec[3] = make_float4(radii, __uint_as_float(P.index_base + i), 0.f, 0.f);  // global Gaussian index (the sort payload of the reference)
         P.dkeys[cid] = __float_as_uint(depth);  // depth > 0.2: the IEEE bits are monotone as unsigned
         P.dvals[cid] = cid;
+    }
     }
     if (DEBUG && i < P.n) {
         P.dbg_tiles[i] = nt;
@@ -700,8 +795,9 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_EMIT_MIN_BLOCKS) k_emit_cull(
 cudaError_t launch_project(const ProjectParams& p, bool debug, cudaStream_t s) {
     if (p.n == 0) return cudaSuccess;
     const unsigned blocks = (p.n + PRE_THREADS - 1) / PRE_THREADS;
-    if (debug) k_project<true><<<blocks, PRE_THREADS, 0, s>>>(p);
-    else k_project<false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    if (p.route_world > 0) k_project<false, true><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else if (debug) k_project<true, false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else k_project<false, false><<<blocks, PRE_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

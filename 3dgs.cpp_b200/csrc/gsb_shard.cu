@@ -6,12 +6,13 @@
 //     that slice (k_project is the frame's bandwidth-heaviest kernel; replicating it caps the speed-up at ~2x);
 //   * the FRAME is sharded by tile rows: rank d blends band d (equal-height bands of R = ceil(tiles_y / G) tile rows).
 // Between the two sits ONE exchange over peer memory, fused into the kernels on either side instead of a collective:
-//   k_route   every cull survivor of the local slice is delivered -- its 64-B record with the AABB clipped to the band, and
-//             its depth key -- into the exchange buffers of every rank whose band its AABB touches, by plain stores into peer-mapped
-//             memory (NVLink).  Slots are deterministic: rank d's buffer is divided into G regions of S slots, region s
-//             receives rank s's survivors in Gaussian-index order (a G-wide decoupled look-back scan on the source), so
-//             the band's survivor list is in global index order exactly like k_project's compaction on one GPU, and the
-//             band's pixels are bit-identical to the single-GPU frame.
+//   k_project (ROUTED, gsb_preprocess.cu) every cull survivor of the local slice is delivered straight from the projection's
+//             registers -- its 64-B record with the AABB clipped to the band, and its depth key -- into the exchange buffers
+//             of every rank whose band its AABB touches, by plain stores into peer-mapped memory (NVLink).  Slots are
+//             deterministic: rank d's buffer is divided into G regions of S slots, region s receives rank s's survivors in
+//             Gaussian-index order (G simultaneous decoupled look-back scans on the source), so the band's survivor list is
+//             in global index order exactly like k_project's compaction on one GPU, and the band's pixels are bit-identical
+//             to the single-GPU frame.  (A separate k_route pass over the compacted records cost 0.1-0.2 ms more.)
 //   k_blend2  stores its band straight into the whole-frame buffer of EVERY rank (the all-gather of the framebuffer,
 //             done by the producer's stores; GSB_SHARD_GATHER=nccl replaces it by one in-place ncclAllGather).
 // Cross-GPU ordering uses mailbox words in peer memory: `started` (a rank entered frame f: its buffers of frame f - 2
@@ -81,7 +82,6 @@ struct ShardState {
     uint32_t* dvals_d[2] = {nullptr, nullptr};
     unsigned long long* emit_status_d = nullptr;
     uint32_t* route_status = nullptr;  // [chunks of the slice][GSB_MAX_SHARDS]
-    uint32_t nv_local_hint = 0;
     Mailbox* mailbox_host = nullptr;   // pinned copy of the own mailbox (overflow flags, error) at the end of a frame
     uint32_t last_parity = 0;
 
@@ -107,8 +107,6 @@ struct gsb_group {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int ROUTE_THREADS = 256;
-constexpr uint32_t R_AGG = 1u << 30, R_PREFIX = 2u << 30, R_FLAGS = 3u << 30, R_COUNT = (1u << 30) - 1u;
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -149,130 +147,6 @@ __global__ void k_shard_wait(const uint32_t* words, uint32_t value, int world, u
     }
     __syncwarp();
     __threadfence_system();
-}
-
-struct RouteParams {
-    const uint32_t* d_nv;  // local survivor count (Control::num_visible after k_project)
-    const float4* recs;
-    const uint32_t* dkeys;
-    uint32_t* status;  // [chunks][GSB_MAX_SHARDS]
-    Control* ctl;
-    int world;
-    uint32_t band_rows;  // R: band d = tile rows [d R, (d + 1) R)
-    float4* dst_recs[GSB_MAX_SHARDS];  // region of THIS source inside rank d's exchange buffers
-    uint32_t* dst_dkeys[GSB_MAX_SHARDS];
-};
-
-// Source side of the exchange: G simultaneous stream compactions (one per destination band) of the local survivors,
-// single pass, decoupled look-back over G-wide status vectors, and the stores of the records into peer memory.
-__global__ void __launch_bounds__(ROUTE_THREADS) k_route(const __grid_constant__ RouteParams P) {
-    __shared__ uint32_t s_chunk;
-    __shared__ uint32_t s_wcnt[ROUTE_THREADS / 32][GSB_MAX_SHARDS];
-    __shared__ uint32_t s_base[GSB_MAX_SHARDS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nv = *P.d_nv;
-    const uint32_t num_chunks = (nv + ROUTE_THREADS - 1) / ROUTE_THREADS;
-    const int G = P.world;
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_chunk = atomicAdd(&P.ctl->route_ticket, 1u);
-        __syncthreads();
-        const uint32_t chunk = s_chunk;
-        if (chunk >= num_chunks) break;
-        const uint32_t j = chunk * ROUTE_THREADS + tid;
-        uint32_t y0 = 0, y1 = 0;
-        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nv) {
-            q1 = __ldg(P.recs + (size_t)j * GSB_REC_F4 + 1);  // conic.z, opacity, whole-frame tile AABB
-            y0 = __float_as_uint(q1.z) >> 16;
-            y1 = y0 + (__float_as_uint(q1.w) >> 16);
-        }
-        // per destination: does the AABB touch band d, rank among the warp's lanes that do
-        uint32_t touch = 0, rank_w[GSB_MAX_SHARDS];
-#pragma unroll
-        for (int d = 0; d < GSB_MAX_SHARDS; d++) {
-            rank_w[d] = 0;
-            if (d < G) {
-                const uint32_t b0 = (uint32_t)d * P.band_rows, b1 = b0 + P.band_rows;
-                const bool t = max(y0, b0) < min(y1, b1);
-                const unsigned bits = __ballot_sync(FULL, t);
-                if (t) touch |= 1u << d;
-                rank_w[d] = __popc(bits & ((1u << lane) - 1u));
-                if (lane == 0) s_wcnt[warp][d] = __popc(bits);
-            }
-        }
-        __syncthreads();
-        uint32_t before[GSB_MAX_SHARDS];
-        if (tid < G) {  // thread d: exclusive scan over the warps, chunk total, publish the aggregate
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < ROUTE_THREADS / 32; w++) {
-                const uint32_t c = s_wcnt[w][tid];
-                s_wcnt[w][tid] = run;
-                run += c;
-            }
-            s_base[tid] = run;  // chunk total for now
-            *reinterpret_cast<volatile uint32_t*>(P.status + (size_t)chunk * GSB_MAX_SHARDS + tid) = (chunk == 0 ? R_PREFIX : R_AGG) | run;
-        }
-        __syncthreads();
-        // decoupled look-back: warp 0, lane = predecessor, one destination at a time (G <= 8, chunks are few)
-        if (warp == 0) {
-            for (int d = 0; d < G; d++) {
-                const uint32_t total = s_base[d];
-                uint32_t ex = 0;
-                if (chunk != 0) {
-                    int look = (int)chunk - 1;
-                    while (true) {
-                        const int idx = look - lane;
-                        uint32_t st = R_PREFIX;
-                        if (idx >= 0) {
-                            st = ld_vol(P.status + (size_t)idx * GSB_MAX_SHARDS + d);
-                            while ((st & R_FLAGS) == 0) st = ld_vol(P.status + (size_t)idx * GSB_MAX_SHARDS + d);
-                        }
-                        const unsigned pm = __ballot_sync(FULL, (st & R_FLAGS) == R_PREFIX);
-                        const int first = pm ? (__ffs(pm) - 1) : 32;
-                        uint32_t cs = (lane <= first) ? (st & R_COUNT) : 0u;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(FULL, cs, o);
-                        ex += cs;
-                        if (pm) break;
-                        look -= 32;
-                    }
-                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(P.status + (size_t)chunk * GSB_MAX_SHARDS + d) = R_PREFIX | (ex + total);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    s_base[d] = ex;
-                    if (chunk == num_chunks - 1) P.ctl->route_total[d] = ex + total;
-                }
-                __syncwarp();
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int d = 0; d < GSB_MAX_SHARDS; d++) before[d] = d < G ? s_base[d] + s_wcnt[warp][d] : 0u;
-        if (touch) {
-            const float4 q0 = __ldg(P.recs + (size_t)j * GSB_REC_F4), q2 = __ldg(P.recs + (size_t)j * GSB_REC_F4 + 2),
-                         q3 = __ldg(P.recs + (size_t)j * GSB_REC_F4 + 3);
-            const uint32_t dk = __ldg(P.dkeys + j);
-#pragma unroll
-            for (int d = 0; d < GSB_MAX_SHARDS; d++) {
-                if (d < G && ((touch >> d) & 1u)) {
-                    const uint32_t pos = before[d] + rank_w[d];
-                    const uint32_t b0 = (uint32_t)d * P.band_rows, b1 = b0 + P.band_rows;
-                    const uint32_t cy0 = max(y0, b0), cy1 = min(y1, b1);  // the band clip k_project applies on one GPU
-                    float4* dst = P.dst_recs[d] + (size_t)pos * GSB_REC_F4;
-                    dst[0] = q0;
-                    dst[1] = make_float4(q1.x, q1.y, __uint_as_float((__float_as_uint(q1.z) & 0xffffu) | (cy0 << 16)),
-                                         __uint_as_float((__float_as_uint(q1.w) & 0xffffu) | ((cy1 - cy0) << 16)));
-                    dst[2] = q2;
-                    dst[3] = q3;
-                    P.dst_dkeys[d][pos] = dk;
-                }
-            }
-        }
-        __threadfence_system();
-    }
 }
 
 struct GatherParams {
@@ -446,8 +320,8 @@ PeerWords words_of(ShardState* sh, size_t field_offset, int index_is_rank, int p
 constexpr long long WAIT_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s at 1.9 GHz: a dead peer becomes an error, not a hung GPU
 
 // One sharded frame is enqueued in four phases; a phase ends where the stream would next WAIT for the other ranks:
-//   1  frame start, signal `started`, k_project over the local slice
-//   2  wait `started`, k_route (stores into peer memory), signal `routed`
+//   1  frame start, signal `started`
+//   2  wait `started`, k_project over the local slice (its survivors are stored straight into peer memory), signal `routed`
 //   3  wait `routed`, gather, depth sort / emission / tile sort, blend (peer stores), signal `framed`
 //   4  wait `framed`, mailbox + stats copy, completion event
 // A process that drives ONE rank enqueues 1-4 back to back.  A group that drives every rank from one host thread enqueues
@@ -493,43 +367,36 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
         if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
         // S1: I have entered frame f (my buffers of parity f & 1 -- last used by frame f - 2 -- may be overwritten)
         k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, started), 1, 0), F.f, G, PeerWords{}, nullptr, 0);
-        // ---- k_project over the local slice, whole frame (no band clip): source-side compaction ----
+        CK(cudaGetLastError());
+        return GSB_OK;
+    }
+    if (phase == 2) {
+        // ---- wait until every rank has entered the frame, then k_project over the local slice (whole frame, no band clip)
+        // delivers every survivor straight into the exchange buffers of the ranks whose band it touches, and announces it ----
+        k_shard_wait<<<1, 32, 0, stream>>>(mb->started, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
         ProjectParams pp{};
         pp.pos_op = ctx->pos_op;
         pp.cov_a = ctx->cov_a;
         pp.cov_b = ctx->cov_b;
         pp.sh = ctx->sh;
-        pp.n = (uint32_t)n_local;
+        pp.n = (uint32_t)ctx->n;
         pp.index_base = (uint32_t)((uint64_t)r * sh->slice);
-        pp.ubo = *ubo;
+        pp.ubo = F.ubo;
         pp.tile_row_begin = 0;
         pp.tile_row_end = F.tiles_y;
-        pp.recs = ctx->recs;
+        pp.recs = ctx->recs;      // unused by the routed kernel
         pp.dkeys = ctx->dkeys[0];
         pp.dvals = ctx->dvals[0];
         pp.status = ctx->project_status;
         pp.ctl = ctx->ctl;
-        CK(launch_project(pp, false, stream));
-        return GSB_OK;
-    }
-    if (phase == 2) {
-        // ---- exchange: wait until every rank has entered the frame, deliver, announce ----
-        k_shard_wait<<<1, 32, 0, stream>>>(mb->started, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
-        RouteParams rp{};
-        rp.d_nv = &ctx->ctl->num_visible;
-        rp.recs = ctx->recs;
-        rp.dkeys = ctx->dkeys[0];
-        rp.status = sh->route_status;
-        rp.ctl = ctx->ctl;
-        rp.world = G;
-        rp.band_rows = std::max(F.R, 1u);
+        pp.route_world = G;
+        pp.band_rows = std::max(F.R, 1u);
+        pp.route_status = sh->route_status;
         for (int d = 0; d < G; d++) {
-            rp.dst_recs[d] = sh->recs_x(d, F.par) + (size_t)r * sh->slice * GSB_REC_F4;
-            rp.dst_dkeys[d] = sh->dkeys_x(d, F.par) + (size_t)r * sh->slice;
+            pp.route_dst_recs[d] = sh->recs_x(d, F.par) + (size_t)r * sh->slice * GSB_REC_F4;
+            pp.route_dst_dkeys[d] = sh->dkeys_x(d, F.par) + (size_t)r * sh->slice;
         }
-        const uint32_t hint = sh->nv_local_hint ? sh->nv_local_hint : (uint32_t)ctx->n;
-        const uint32_t blocks = std::min<uint32_t>((quantise_hint(hint) + ROUTE_THREADS - 1) / ROUTE_THREADS, (uint32_t)ctx->num_sms * 4u);
-        k_route<<<std::max(blocks, 1u), ROUTE_THREADS, 0, stream>>>(rp);
+        CK(launch_project(pp, false, stream));
         k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, routed), 1, 0), F.f, G,
                                              words_of(sh, offsetof(Mailbox, count), 1, F.par * GSB_MAX_SHARDS), ctx->ctl->route_total, 1);
         CK(cudaGetLastError());
@@ -633,7 +500,6 @@ int sharded_frame_status(gsb_ctx* ctx, bool* any_overflow) {
     }
     for (int p = 0; p < sh->world; p++)
         if (sh->mailbox_host->overflow[sh->last_parity][p]) *any_overflow = true;
-    sh->nv_local_hint = 0;  // k_route's grid covers the slice anyway (ticket loop)
     return GSB_OK;
 }
 
