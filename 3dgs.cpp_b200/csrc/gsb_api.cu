@@ -170,7 +170,8 @@ int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool 
     EmitParams ep{};
     ep.sorted_cid = ctx->dvals[fin_a];
     ep.nv_hint = fp.nv_q;
-    ep.tiles_x = fp.tiles_x;
+    ep.tiles_x = fp.bins_x;
+    ep.coarse_shift = fp.cs;
     ep.keys = ctx->keys[0];
     ep.vals = ctx->vals[0];
     ep.capacity = (uint32_t)ctx->capacity;
@@ -178,7 +179,7 @@ int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool 
     ep.ctl = ctx->ctl;
     ep.num_sms = ctx->num_sms;
     ep.recs = ctx->recs;
-    ep.cull = ctx->tile_cull ? 1 : 0;
+    ep.cull = (ctx->tile_cull == 1 && fp.cs == 0) ? 1 : 0;
     ep.dbg_offsets = ctx->debug ? ctx->dbg_offsets : nullptr;
     CK(launch_emit(ep, stream));
     if (events) CK(cudaEventRecord(ctx->ev[3], stream));
@@ -205,7 +206,7 @@ int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool 
     sp.key_bytes = 4;
     sp.d_m = &ctx->ctl->num_instances;
     sp.m_hint = fp.m_q;
-    sp.key_bits = bits_for(fp.T);
+    sp.key_bits = bits_for(fp.bins);
     sp.status = ctx->sort_status;
     sp.status_tiles = ctx->sort_status_tiles;
     sp.d_epoch = &ctx->ctl->epoch;
@@ -231,7 +232,8 @@ int launch_middle_graph(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream) 
     key.num_tiles = fp.T;
     key.nv_q = fp.nv_q;
     key.m_q = fp.m_q;
-    key.cull = ctx->tile_cull ? 1u : 0u;
+    key.cull = (uint32_t)ctx->tile_cull;
+    key.cs = fp.cs;
     key.tag = ctx->middle_tag;
     key.alloc_gen = ctx->alloc_gen;
     MiddleGraph* slot = nullptr;
@@ -297,8 +299,13 @@ int plan_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
     const uint32_t n = (uint32_t)ctx->n;
     fp.nv_q = std::min<uint32_t>(quantise_hint(ctx->nv_hint ? ctx->nv_hint : n), quantise_hint(n));
     fp.m_q = quantise_hint(ctx->m_hint ? ctx->m_hint : std::min<uint64_t>(ctx->capacity, 4u * 1024 * 1024));
+    // gsb_set_tile_cull level 2: the instance sort bins by blocks of 2^cs x 2^cs tiles; every tile of a block walks the block's
+    // list and keeps the records whose AABB holds the tile (k_blend2).  Debug downloads expose per-tile lists: level 2 is off then.
+    fp.cs = (ctx->tile_cull == 2 && !ctx->debug && ctx->blend_variant == 2) ? ctx->coarse_shift : 0u;
+    fp.bins_x = (fp.tiles_x + (1u << fp.cs) - 1) >> fp.cs;
+    fp.bins = fp.bins_x * ((fp.tiles_y + (1u << fp.cs) - 1) >> fp.cs);
     fp.depth_passes = 4;
-    fp.passes = (bits_for(fp.T) + 7) / 8;
+    fp.passes = (bits_for(fp.bins) + 7) / 8;
     fp.fin = (int)(fp.passes & 1);
     if (++ctx->frames_since_epoch_clear >= (1u << 27)) {  // epoch wrap (2^32 / 16 frames): clear the look-back tags once
         CK(cudaMemsetAsync(ctx->sort_status, 0, (size_t)ctx->sort_status_tiles * 256 * sizeof(unsigned long long), stream));
@@ -358,6 +365,8 @@ int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, v
     bp.width = fp.W;
     bp.height = fp.H;
     bp.tiles_x = fp.tiles_x;
+    bp.coarse_shift = fp.cs;
+    bp.bins_x = fp.bins_x;
     bp.tile_row_begin = b0;
     bp.tile_row_end = b1;
     bp.out = static_cast<unsigned char*>(band_out) + (size_t)(b0 - fp.rb) * GSB_TILE * pitch;
@@ -476,6 +485,7 @@ int gsb_create(int device, gsb_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* v = getenv("GSB_BLEND_VARIANT")) ctx->blend_variant = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("GSB_HOST_DIRECT")) ctx->host_direct = atoi(v) != 0;
+    if (const char* v = getenv("GSB_COARSE_SHIFT")) ctx->coarse_shift = (uint32_t)std::min(4, std::max(1, atoi(v)));
     if ((e = sort_prepare()) != cudaSuccess) return bail("sort_prepare", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = dev_alloc(&ctx->ctl, 1)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -652,9 +662,9 @@ void gsb_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int gsb_set_tile_cull(gsb_ctx* ctx, int enabled) {
-    if (!ctx) return GSB_ERR_INVALID;
-    ctx->tile_cull = enabled != 0;
+int gsb_set_tile_cull(gsb_ctx* ctx, int level) {
+    if (!ctx || level < 0 || level > 2) return GSB_ERR_INVALID;
+    ctx->tile_cull = level;
     return GSB_OK;
 }
 

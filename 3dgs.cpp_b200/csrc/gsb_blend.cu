@@ -414,7 +414,11 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tx = blockIdx.x % P.tiles_x;
     const uint32_t ty = P.tile_row_begin + blockIdx.x / P.tiles_x;
-    uint2 range = P.ranges[ty * P.tiles_x + tx];  // render.comp:43-44; stored as (start, ~end), empty = all ones
+    // render.comp:43-44; stored as (start, ~end), empty = all ones.  With coarse bins (gsb_set_tile_cull level 2) the list is
+    // that of the 2^cs x 2^cs tile block holding this tile: still in (depth, index) order, and the staging below keeps exactly
+    // the records whose tile AABB holds (tx, ty) = the tile's own list in the reference.
+    const uint32_t cs = P.coarse_shift;
+    uint2 range = P.ranges[(ty >> cs) * P.bins_x + (tx >> cs)];
     range.y = ~range.y;
     const uint32_t px = tx * GSB_TILE + (warp & 1) * 8 + (lane & 7);
     const uint32_t py0 = ty * GSB_TILE + (warp >> 1) * 8 + (lane >> 3), py1 = py0 + 4;
@@ -444,16 +448,25 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             if (li < cnt) {
                 const uint32_t cid = __ldg(P.vals + base + li);
                 const float4* rec = P.recs + (size_t)cid * GSB_REC_F4;
-                const float4 a = __ldg(rec), col = __ldg(rec + 2);
-                const float2 b = __ldg(reinterpret_cast<const float2*>(rec + 1));  // conic.z, opacity
-                const float cut = power_cut(b.y);
-                const float na = -0.5f * a.z, nb = -a.w, nc = -0.5f * b.x;
-                s_rec[li].q0 = make_float4(a.x, a.x, a.y, a.y);
-                s_rec[li].q1 = make_float4(na, na, nb, nb);
-                s_rec[li].q2 = make_float4(nc, nc, b.y, b.y);
-                s_rec[li].q3 = make_float4(col.x, col.x, col.y, col.y);
-                s_rec[li].q4 = make_float4(col.z, col.z, cut, __uint_as_float(li));
-                s_mask[li] = (uint8_t)block_mask2(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
+                const float4 b = __ldg(rec + 1);  // conic.z, opacity, tile AABB
+                // coarse bins: is this tile inside the Gaussian's tile AABB (preprocess_sort.comp:47-48 emits exactly those)?
+                const uint32_t bxy = __float_as_uint(b.z), bwh = __float_as_uint(b.w);
+                const bool here = cs == 0 || ((tx - (bxy & 0xffffu)) < (bwh & 0xffffu) && (ty - (bxy >> 16)) < (bwh >> 16));
+                uint32_t m = 0;
+                if (here) {
+                    const float4 a = __ldg(rec), col = __ldg(rec + 2);
+                    const float cut = power_cut(b.y);
+                    m = block_mask2(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
+                    if (m) {
+                        const float na = -0.5f * a.z, nb = -a.w, nc = -0.5f * b.x;
+                        s_rec[li].q0 = make_float4(a.x, a.x, a.y, a.y);
+                        s_rec[li].q1 = make_float4(na, na, nb, nb);
+                        s_rec[li].q2 = make_float4(nc, nc, b.y, b.y);
+                        s_rec[li].q3 = make_float4(col.x, col.x, col.y, col.y);
+                        s_rec[li].q4 = make_float4(col.z, col.z, cut, __uint_as_float(li));
+                    }
+                }
+                s_mask[li] = (uint8_t)m;
             }
         }
         __syncthreads();
@@ -640,7 +653,7 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t s) {
     const uint32_t rows = p.tile_row_end - p.tile_row_begin;
     const uint32_t blocks = rows * p.tiles_x;
     if (blocks == 0) return cudaSuccess;
-    if (p.variant == 1 && p.num_peers == 0) {  // round-1 kernel (one pixel per thread), kept for A/B: GSB_BLEND_VARIANT=1
+    if (p.variant == 1 && p.num_peers == 0 && p.coarse_shift == 0) {  // round-1 kernel (one pixel per thread), kept for A/B: GSB_BLEND_VARIANT=1
         if (p.mode == GSB_MODE_EXACT) k_blend<GSB_MODE_EXACT><<<blocks, BLEND_THREADS, 0, s>>>(p);
         else k_blend<GSB_MODE_FAST><<<blocks, BLEND_THREADS, 0, s>>>(p);
     } else if (p.stats) {

@@ -14,10 +14,11 @@ using gsb::Control;
 // Captured CUDA graph of the "middle" of a frame (depth sort, key emission, tile sort: 9-10 kernels whose arguments do
 // not depend on the camera).  Replaces recordRenderCommandBuffer's pre-recorded command buffer (src/Renderer.cpp:532-717).
 struct MiddleKey {
-    uint32_t tiles_x = 0, num_tiles = 0, nv_q = 0, m_q = 0, cull = 0, tag = 0;
+    uint32_t tiles_x = 0, num_tiles = 0, nv_q = 0, m_q = 0, cull = 0, tag = 0, cs = 0;
     uint64_t alloc_gen = 0;
     bool operator==(const MiddleKey& o) const {
-        return tiles_x == o.tiles_x && num_tiles == o.num_tiles && nv_q == o.nv_q && m_q == o.m_q && cull == o.cull && tag == o.tag && alloc_gen == o.alloc_gen;
+        return tiles_x == o.tiles_x && num_tiles == o.num_tiles && nv_q == o.nv_q && m_q == o.m_q && cull == o.cull && tag == o.tag &&
+               cs == o.cs && alloc_gen == o.alloc_gen;
     }
 };
 struct MiddleGraph {
@@ -62,7 +63,8 @@ struct gsb_ctx {
     int mode = GSB_MODE_EXACT;
     bool debug = false;
     bool timers = true;
-    bool tile_cull = false;
+    int tile_cull = 0;          // gsb_set_tile_cull level: 0 reference-equivalent lists, 1 exact per-tile culling, 2 coarse bins
+    uint32_t coarse_shift = 2;  // level 2 bins are 2^shift x 2^shift tiles (GSB_COARSE_SHIFT)
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_sort[9] = {};  // instance sort: after hist, after each pass
     cudaEvent_t ev_done = nullptr;
@@ -120,6 +122,7 @@ void dev_free(T*& p) {
 
 struct FramePlan {
     uint32_t W, H, tiles_x, tiles_y, T, rb, re;
+    uint32_t cs, bins_x, bins;  // instance-sort bins: 2^cs x 2^cs tile blocks (cs = 0: the tiles themselves, bins == T)
     uint32_t nv_q, m_q, depth_passes, passes;
     int fin;
 };

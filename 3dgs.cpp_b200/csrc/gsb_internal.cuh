@@ -94,7 +94,8 @@ struct EmitParams {
     Control* ctl;
     int num_sms;
     const float4* recs;          // survivor records: tile AABB (+ centre, conic, opacity for the optional instance culling)
-    int cull;                    // gsb_set_tile_cull
+    int cull;                    // gsb_set_tile_cull level 1: exact per-tile instance culling (k_emit_cull)
+    uint32_t coarse_shift;       // gsb_set_tile_cull level 2: bin by 2^shift x 2^shift tile blocks (tiles_x = bins per row); 0 = by tile
     unsigned long long* dbg_offsets;  // debug (may be null): exclusive instance offset of each depth-sorted survivor
 };
 
@@ -137,6 +138,7 @@ struct BlendParams {
     const uint32_t* vals;
     const uint2* ranges;
     uint32_t width, height, tiles_x;
+    uint32_t coarse_shift, bins_x;  // the sorted lists and `ranges` are per 2^shift x 2^shift tile block (0: per tile), bins_x blocks per row
     uint32_t tile_row_begin, tile_row_end;
     void* out;              // pixel row `out_first_row` of the frame lives at out + 0
     uint32_t out_first_row; // 16 * tile_row_begin for a band buffer, 0 for a whole-frame buffer

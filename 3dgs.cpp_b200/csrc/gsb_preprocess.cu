@@ -427,22 +427,33 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
         if (chunk >= num_chunks) break;
         const uint32_t j = chunk * PRE_THREADS + tid;
 
-        uint32_t nt = 0, cid = 0, xy = 0, wh = 0;
+        uint32_t nt = 0, cand = 0, cid = 0, xy = 0, wh = 0;
         if (j < nv) {
             cid = __ldg(P.sorted_cid + j);
             const float4 q1 = __ldg(P.recs + (size_t)cid * GSB_REC_F4 + 1);
             xy = __float_as_uint(q1.z);
             wh = __float_as_uint(q1.w);
+            cand = (wh & 0xffffu) * (wh >> 16);  // tiles of the AABB = the reference's instance count for this Gaussian
+            if (P.coarse_shift != 0 && cand != 0) {  // gsb_set_tile_cull level 2: emit the 2^cs x 2^cs tile blocks the AABB touches
+                const uint32_t cs = P.coarse_shift;
+                const uint32_t x0 = xy & 0xffffu, y0 = xy >> 16, x1 = x0 + (wh & 0xffffu), y1 = y0 + (wh >> 16);
+                const uint32_t cx0 = x0 >> cs, cy0 = y0 >> cs, cx1 = ((x1 - 1) >> cs) + 1, cy1 = ((y1 - 1) >> cs) + 1;
+                xy = cx0 | (cy0 << 16);
+                wh = (cx1 - cx0) | ((cy1 - cy0) << 16);
+            }
             nt = (wh & 0xffffu) * (wh >> 16);
         }
         // ---- block scan of the tile counts (prefix_sum.comp's job) ----
-        uint32_t nt_incl = nt;
+        uint32_t nt_incl = nt, cand_sum = cand;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(FULL, nt_incl, o);
             if (lane >= o) nt_incl += t;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand_sum += __shfl_xor_sync(FULL, cand_sum, o);
         if (lane == 31) s_wnt[warp] = nt_incl;
+        if (lane == 0 && cand_sum) atomicAdd(&P.ctl->candidates_total, (unsigned long long)cand_sum);
         __syncthreads();
         uint32_t nt_before = 0, blk_nt = 0;
 #pragma unroll
@@ -452,10 +463,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
             blk_nt += b;
         }
         const uint32_t off = nt_before + (nt_incl - nt);  // exclusive offset inside the chunk
-        if (tid == 0) {
-            st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
-            atomicAdd(&P.ctl->candidates_total, (unsigned long long)blk_nt);
-        }
+        if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
         if (nt > EMIT_BIG) {
             s_info[tid] = make_uint4(xy, wh, off, cid);
             s_big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;

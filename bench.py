@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 extra workload measured at --gpus 4 / 8")
-    ap.add_argument("--tile-cull", type=int, default=1, help="gsb_set_tile_cull (exact instance culling; image bit-identical)")
+    ap.add_argument("--tile-cull", type=int, default=1, help="gsb_set_tile_cull level: 0 reference lists, 1 exact per-tile instance culling, 2 coarse bins (image bit-identical in all three)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -269,7 +269,7 @@ def main():
     else:
         ctx = g.Context(local_rank)
     ctx.set_mode(g.MODE_EXACT if args.mode == "exact" else g.MODE_FAST)
-    ctx.set_tile_cull(bool(args.tile_cull))
+    ctx.set_tile_cull(int(args.tile_cull))
 
     env = dict(g=g, torch=torch, dist=dist, dev=dev, rank=rank, world=world, local_rank=local_rank, ctx=ctx, args=args)
     out = measure(env, wl_name, wl, args.steps, max(3, args.warmup), headline=True)
@@ -499,7 +499,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {**bench_config(wl_name, wl),
-                   "instances_M": M, "instances_aabb": float(np.mean(aabb_acc)), "tile_cull": bool(args.tile_cull), "visible": NV,
+                   "instances_M": M, "instances_aabb": float(np.mean(aabb_acc)), "tile_cull": int(args.tile_cull), "visible": NV,
                    "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8", "scene_load_s": t_load,
                    "l2": "inputs (scene + sort keys, > 1 GB) larger than the 126 MB L2; 8 camera poses alternate; no flush",
                    "parallelism": (f"scene sharded by Gaussian index x{world}, frame by tile-row bands x{world}; survivors and framebuffer "
