@@ -179,7 +179,7 @@ int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool 
     ep.ctl = ctx->ctl;
     ep.num_sms = ctx->num_sms;
     ep.recs = ctx->recs;
-    ep.cull = (ctx->tile_cull == 1 && fp.cs == 0) ? 1 : 0;
+    ep.cull = (ctx->tile_cull >= 1 && fp.cs == 0) ? 1 : 0;  // level 2 falls back to level 1 where coarse bins are unavailable
     ep.dbg_offsets = ctx->debug ? ctx->dbg_offsets : nullptr;
     CK(launch_emit(ep, stream));
     if (events) CK(cudaEventRecord(ctx->ev[3], stream));
@@ -215,7 +215,9 @@ int enqueue_middle(gsb_ctx* ctx, const FramePlan& fp, cudaStream_t stream, bool 
     sp.num_sms = ctx->num_sms;
     sp.events = events ? ctx->ev_sort : nullptr;
     sp.ranges = ctx->ranges;  // the last pass writes the tile ranges (tile_boundary.comp fused)
-    sp.discard_sorted_keys = !ctx->debug;  // only gsb_debug_download(GSB_BUF_KEYS) reads them; the blend uses vals + ranges
+    // the fully sorted keys are read by gsb_debug_download(GSB_BUF_KEYS) and, with coarse bins, by the blend (tile masks)
+    sp.discard_sorted_keys = !ctx->debug && fp.cs == 0;
+    sp.range_key_mask = fp.cs ? 0xffffu : 0u;
     uint32_t passes = 0;
     CK(launch_sort(sp, &passes, stream));
     if (events) CK(cudaEventRecord(ctx->ev[4], stream));
@@ -304,6 +306,11 @@ int plan_frame(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uint32_t re, 
     fp.cs = (ctx->tile_cull == 2 && !ctx->debug && ctx->blend_variant == 2) ? ctx->coarse_shift : 0u;
     fp.bins_x = (fp.tiles_x + (1u << fp.cs) - 1) >> fp.cs;
     fp.bins = fp.bins_x * ((fp.tiles_y + (1u << fp.cs) - 1) >> fp.cs);
+    if (fp.cs && fp.bins > 65536u) {  // the block id must fit the 16 key bits below the tile mask (8K x 4K frames still do)
+        fp.cs = 0;
+        fp.bins_x = fp.tiles_x;
+        fp.bins = fp.T;
+    }
     fp.depth_passes = 4;
     fp.passes = (bits_for(fp.bins) + 7) / 8;
     fp.fin = (int)(fp.passes & 1);
@@ -361,6 +368,7 @@ int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, v
     BlendParams bp{};
     bp.recs = ctx->recs;
     bp.vals = ctx->vals[fp.fin];
+    bp.keys = ctx->keys[fp.fin];
     bp.ranges = ctx->ranges;
     bp.width = fp.W;
     bp.height = fp.H;
@@ -485,7 +493,7 @@ int gsb_create(int device, gsb_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* v = getenv("GSB_BLEND_VARIANT")) ctx->blend_variant = atoi(v) == 1 ? 1 : 2;
     if (const char* v = getenv("GSB_HOST_DIRECT")) ctx->host_direct = atoi(v) != 0;
-    if (const char* v = getenv("GSB_COARSE_SHIFT")) ctx->coarse_shift = (uint32_t)std::min(4, std::max(1, atoi(v)));
+    if (const char* v = getenv("GSB_COARSE_SHIFT")) ctx->coarse_shift = (uint32_t)std::min(2, std::max(1, atoi(v)));  // 2x2 or 4x4 tiles: the mask has 16 bits
     if ((e = sort_prepare()) != cudaSuccess) return bail("sort_prepare", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = dev_alloc(&ctx->ctl, 1)) != cudaSuccess) return bail("cudaMalloc", e);

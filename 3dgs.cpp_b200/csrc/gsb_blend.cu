@@ -403,10 +403,18 @@ __device__ __forceinline__ void exp_shared2(u64 x, u64 one2, float& e0, float& e
     e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(m1) << 23));
 }
 
-template <int MODE, bool STATS>
+// COARSE (gsb_set_tile_cull level 2): the list is that of a block of 2^cs x 2^cs tiles and every entry's key carries the mask
+// of the block's tiles inside the Gaussian's tile AABB.  Staging becomes a stream compaction: the CTA scans the list 128
+// entries at a time (keys + payloads only, coalesced), keeps the entries whose mask has this tile's bit -- in list order, so
+// the tile's own (depth, index) order is preserved -- and gathers records only for those, until the batch holds up to
+// B2_BATCH of them.  The walk is unchanged.
+template <int MODE, bool STATS, bool COARSE>
 __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(const __grid_constant__ BlendParams P) {
     __shared__ StagedRec2 s_rec[B2_BATCH];
     __shared__ uint8_t s_mask[B2_BATCH];
+    __shared__ uint32_t s_cid[COARSE ? B2_BATCH : 1];   // COARSE: compact id and list position of the batch's entries
+    __shared__ uint32_t s_eidx[COARSE ? B2_BATCH : 1];
+    __shared__ uint32_t s_wc[B2_WARPS];
     __shared__ uint16_t s_list[B2_WARPS][B2_BATCH];  // per warp: shared-window addresses of the records it must visit
     __shared__ uint32_t s_used, s_walked, s_hits;
     static_assert(sizeof(StagedRec2) * B2_BATCH < 65536, "u16 list entries hold shared-window addresses");
@@ -440,31 +448,70 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);
     const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
 
-    for (uint32_t base = range.x; base < range.y; base += B2_BATCH) {
-        const uint32_t cnt = min((uint32_t)B2_BATCH, range.y - base);
+    const uint32_t tbit = 16u + (((ty & ((1u << cs) - 1u)) << cs) | (tx & ((1u << cs) - 1u)));  // this tile's bit in a coarse key
+    uint32_t cursor = range.x;  // COARSE: next list entry to scan
+    for (uint32_t base = range.x; COARSE ? (cursor < range.y) : (base < range.y); base += B2_BATCH) {
+        uint32_t cnt;
+        if constexpr (COARSE) {
+            // ---- fill: scan up to 4 x 128 entries (loads issued together), compact this tile's entries in list order ----
+            constexpr int STEPS = 4;
+            uint32_t kk[STEPS], vv[STEPS];
+#pragma unroll
+            for (int j = 0; j < STEPS; j++) {
+                const uint32_t e = cursor + (uint32_t)(j * B2_THREADS + tid);
+                kk[j] = 0u;
+                vv[j] = 0u;
+                if (e < range.y) {
+                    kk[j] = __ldg(P.keys + e);
+                    vv[j] = __ldg(P.vals + e);
+                }
+            }
+            uint32_t nfill = 0, steps = 0;
+#pragma unroll
+            for (int j = 0; j < STEPS; j++) {
+                if (cursor + (uint32_t)(j * B2_THREADS) >= range.y || nfill > (uint32_t)(B2_BATCH - B2_THREADS)) break;  // uniform
+                const bool match = (kk[j] >> tbit) & 1u;
+                const unsigned bits = __ballot_sync(FULL, match);
+                if (lane == 0) s_wc[warp] = __popc(bits);
+                __syncthreads();
+                uint32_t off = nfill + __popc(bits & ((1u << lane) - 1u)), tot = 0;
+#pragma unroll
+                for (int w = 0; w < B2_WARPS; w++) {
+                    const uint32_t c = s_wc[w];
+                    if (w < warp) off += c;
+                    tot += c;
+                }
+                if (match) {
+                    s_cid[off] = vv[j];
+                    s_eidx[off] = cursor - range.x + (uint32_t)(j * B2_THREADS + tid);
+                }
+                nfill += tot;
+                steps++;
+                __syncthreads();  // s_wc is reused by the next step; s_cid / s_eidx are read below
+            }
+            cursor = min(range.y, cursor + steps * (uint32_t)B2_THREADS);
+            cnt = nfill;
+        } else {
+            cnt = min((uint32_t)B2_BATCH, range.y - base);
+        }
 #pragma unroll
         for (int j = 0; j < B2_BATCH / B2_THREADS; j++) {
             const uint32_t li = (uint32_t)(j * B2_THREADS + tid);
             if (li < cnt) {
-                const uint32_t cid = __ldg(P.vals + base + li);
+                const uint32_t cid = COARSE ? s_cid[li] : __ldg(P.vals + base + li);
                 const float4* rec = P.recs + (size_t)cid * GSB_REC_F4;
-                const float4 b = __ldg(rec + 1);  // conic.z, opacity, tile AABB
-                // coarse bins: is this tile inside the Gaussian's tile AABB (preprocess_sort.comp:47-48 emits exactly those)?
-                const uint32_t bxy = __float_as_uint(b.z), bwh = __float_as_uint(b.w);
-                const bool here = cs == 0 || ((tx - (bxy & 0xffffu)) < (bwh & 0xffffu) && (ty - (bxy >> 16)) < (bwh >> 16));
-                uint32_t m = 0;
-                if (here) {
-                    const float4 a = __ldg(rec), col = __ldg(rec + 2);
-                    const float cut = power_cut(b.y);
-                    m = block_mask2(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
-                    if (m) {
-                        const float na = -0.5f * a.z, nb = -a.w, nc = -0.5f * b.x;
-                        s_rec[li].q0 = make_float4(a.x, a.x, a.y, a.y);
-                        s_rec[li].q1 = make_float4(na, na, nb, nb);
-                        s_rec[li].q2 = make_float4(nc, nc, b.y, b.y);
-                        s_rec[li].q3 = make_float4(col.x, col.x, col.y, col.y);
-                        s_rec[li].q4 = make_float4(col.z, col.z, cut, __uint_as_float(li));
-                    }
+                const float4 a = __ldg(rec), col = __ldg(rec + 2);
+                const float2 b = __ldg(reinterpret_cast<const float2*>(rec + 1));  // conic.z, opacity
+                const float cut = power_cut(b.y);
+                const uint32_t m = block_mask2(a.x, a.y, a.z, a.w, b.x, cut, tile_x0, tile_y0);
+                if (m) {
+                    const float na = -0.5f * a.z, nb = -a.w, nc = -0.5f * b.x;
+                    s_rec[li].q0 = make_float4(a.x, a.x, a.y, a.y);
+                    s_rec[li].q1 = make_float4(na, na, nb, nb);
+                    s_rec[li].q2 = make_float4(nc, nc, b.y, b.y);
+                    s_rec[li].q3 = make_float4(col.x, col.x, col.y, col.y);
+                    // q4.w: position in the list relative to the batch's base offset (the consumed-entries statistic)
+                    s_rec[li].q4 = make_float4(col.z, col.z, cut, __uint_as_float(COARSE ? s_eidx[li] : li));
                 }
                 s_mask[li] = (uint8_t)m;
             }
@@ -479,7 +526,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
                 n += __popc(bits);
             }
             __syncwarp();
-            const uint32_t base_off = base - range.x;
+            const uint32_t base_off = COARSE ? 0u : base - range.x;
             uint32_t k0 = 0;
             for (; k0 < n; k0 += GSB_BLEND2_CHECK) {
                 if (__all_sync(FULL, B2_DONE)) break;
@@ -582,7 +629,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             }
             if (STATS) {
                 walked += min(k0, n);
-                if (!B2_DONE) used = base_off + cnt;  // a live pixel read the whole batch
+                if (!B2_DONE) used = COARSE ? cursor - range.x : base_off + cnt;  // a live pixel read the whole batch
             }
         }
         if (__syncthreads_and(B2_DONE)) break;
@@ -656,12 +703,20 @@ cudaError_t launch_blend(const BlendParams& p, cudaStream_t s) {
     if (p.variant == 1 && p.num_peers == 0 && p.coarse_shift == 0) {  // round-1 kernel (one pixel per thread), kept for A/B: GSB_BLEND_VARIANT=1
         if (p.mode == GSB_MODE_EXACT) k_blend<GSB_MODE_EXACT><<<blocks, BLEND_THREADS, 0, s>>>(p);
         else k_blend<GSB_MODE_FAST><<<blocks, BLEND_THREADS, 0, s>>>(p);
+    } else if (p.coarse_shift) {
+        if (p.stats) {
+            if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, true, true><<<blocks, B2_THREADS, 0, s>>>(p);
+            else k_blend2<GSB_MODE_FAST, true, true><<<blocks, B2_THREADS, 0, s>>>(p);
+        } else {
+            if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, false, true><<<blocks, B2_THREADS, 0, s>>>(p);
+            else k_blend2<GSB_MODE_FAST, false, true><<<blocks, B2_THREADS, 0, s>>>(p);
+        }
     } else if (p.stats) {
-        if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, true><<<blocks, B2_THREADS, 0, s>>>(p);
-        else k_blend2<GSB_MODE_FAST, true><<<blocks, B2_THREADS, 0, s>>>(p);
+        if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, true, false><<<blocks, B2_THREADS, 0, s>>>(p);
+        else k_blend2<GSB_MODE_FAST, true, false><<<blocks, B2_THREADS, 0, s>>>(p);
     } else {
-        if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, false><<<blocks, B2_THREADS, 0, s>>>(p);
-        else k_blend2<GSB_MODE_FAST, false><<<blocks, B2_THREADS, 0, s>>>(p);
+        if (p.mode == GSB_MODE_EXACT) k_blend2<GSB_MODE_EXACT, false, false><<<blocks, B2_THREADS, 0, s>>>(p);
+        else k_blend2<GSB_MODE_FAST, false, false><<<blocks, B2_THREADS, 0, s>>>(p);
     }
     return cudaGetLastError();
 }

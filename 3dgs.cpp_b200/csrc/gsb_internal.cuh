@@ -119,6 +119,7 @@ struct SortParams {
     int num_sms;
     cudaEvent_t* events;       // optional: events[0] after the histogram, events[1 + p] after pass p
     uint2* ranges;             // optional (u32 keys): the last pass also produces the tile ranges (start, ~end)
+    uint32_t range_key_mask;   // bits of a key that index `ranges` (0 = all; coarse bins keep a tile mask above bit 15)
     bool discard_sorted_keys;  // the last pass writes payloads only (the caller never reads the sorted keys)
 };
 // Returns the number of passes P via *passes; sorted data ends in keys[P & 1].
@@ -136,6 +137,7 @@ cudaError_t launch_ranges_single_tile(const uint32_t* d_m, uint2* ranges, cudaSt
 struct BlendParams {
     const float4* recs;
     const uint32_t* vals;
+    const uint32_t* keys;   // coarse bins only: the sorted keys (block id | tile mask << 16)
     const uint2* ranges;
     uint32_t width, height, tiles_x;
     uint32_t coarse_shift, bins_x;  // the sorted lists and `ranges` are per 2^shift x 2^shift tile block (0: per tile), bins_x blocks per row

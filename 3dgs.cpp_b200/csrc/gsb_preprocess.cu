@@ -402,6 +402,19 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
 constexpr int EMIT_WIN = GSB_EMIT_WIN;   // instances staged in shared memory per window
 constexpr uint32_t EMIT_BIG = 128;  // Gaussians covering more tiles than this are expanded by the whole block
 
+// COARSE (gsb_set_tile_cull level 2): the emitted unit is a block of 2^cs x 2^cs tiles (cs = 1 or 2) instead of a tile.  The key is
+// (block id) | (mask << 16): bit (ly << cs | lx) of the mask says that tile (lx, ly) of the block lies inside the Gaussian's
+// tile AABB, i.e. that preprocess_sort.comp:47-48 would have emitted that (Gaussian, tile) instance.  The radix passes only
+// look at the low 16 bits, the mask rides along, and the blend of a tile keeps exactly the entries whose mask has its bit.
+__device__ __forceinline__ uint32_t coarse_tile_mask(uint32_t cs, uint32_t bx, uint32_t by, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    const uint32_t ox = bx << cs, oy = by << cs, n = 1u << cs;
+    const uint32_t lx0 = max(x0, ox) - ox, lx1 = min(x1, ox + n) - ox, ly0 = max(y0, oy) - oy, ly1 = min(y1, oy + n) - oy;
+    const uint32_t cols = (1u << lx1) - (1u << lx0);                       // tiles lx0 .. lx1-1 of one block row
+    const uint32_t rows = (1u << (ly1 << cs)) - (1u << (ly0 << cs));       // bit ranges of block rows ly0 .. ly1-1
+    return (cols * (cs == 2 ? 0x1111u : 0x5u)) & rows;
+}
+
+template <bool COARSE>
 __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ EmitParams P) {
     __shared__ uint32_t s_chunk;
     __shared__ uint32_t s_wnt[PRE_THREADS / 32];
@@ -409,6 +422,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
     __shared__ uint32_t s_nbig;
     __shared__ uint32_t s_big[PRE_THREADS];  // lanes of the chunk holding "big" Gaussians
     __shared__ uint4 s_info[PRE_THREADS];    // x0 | y0 << 16, w | h << 16, local offset, compact id
+    __shared__ uint2 s_fine[COARSE ? PRE_THREADS : 1];  // COARSE: the tile AABB (x0 | y0 << 16, x1 | y1 << 16) of the big Gaussians
     __shared__ uint32_t s_key[EMIT_WIN];
     __shared__ uint32_t s_val[EMIT_WIN];
 
@@ -416,6 +430,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
     const uint32_t nv = P.ctl->num_visible;
     const uint32_t num_chunks = (nv + PRE_THREADS - 1) / PRE_THREADS;
     const uint32_t tiles_x = P.tiles_x;
+    const uint32_t cs = P.coarse_shift;
 
     while (true) {
         if (tid == 0) {
@@ -428,16 +443,16 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
         const uint32_t j = chunk * PRE_THREADS + tid;
 
         uint32_t nt = 0, cand = 0, cid = 0, xy = 0, wh = 0;
+        uint32_t fx0 = 0, fy0 = 0, fx1 = 0, fy1 = 0;  // COARSE: the tile AABB
         if (j < nv) {
             cid = __ldg(P.sorted_cid + j);
             const float4 q1 = __ldg(P.recs + (size_t)cid * GSB_REC_F4 + 1);
             xy = __float_as_uint(q1.z);
             wh = __float_as_uint(q1.w);
             cand = (wh & 0xffffu) * (wh >> 16);  // tiles of the AABB = the reference's instance count for this Gaussian
-            if (P.coarse_shift != 0 && cand != 0) {  // gsb_set_tile_cull level 2: emit the 2^cs x 2^cs tile blocks the AABB touches
-                const uint32_t cs = P.coarse_shift;
-                const uint32_t x0 = xy & 0xffffu, y0 = xy >> 16, x1 = x0 + (wh & 0xffffu), y1 = y0 + (wh >> 16);
-                const uint32_t cx0 = x0 >> cs, cy0 = y0 >> cs, cx1 = ((x1 - 1) >> cs) + 1, cy1 = ((y1 - 1) >> cs) + 1;
+            if (COARSE && cand != 0) {  // emit the 2^cs x 2^cs tile blocks the AABB touches
+                fx0 = xy & 0xffffu, fy0 = xy >> 16, fx1 = fx0 + (wh & 0xffffu), fy1 = fy0 + (wh >> 16);
+                const uint32_t cx0 = fx0 >> cs, cy0 = fy0 >> cs, cx1 = ((fx1 - 1) >> cs) + 1, cy1 = ((fy1 - 1) >> cs) + 1;
                 xy = cx0 | (cy0 << 16);
                 wh = (cx1 - cx0) | ((cy1 - cy0) << 16);
             }
@@ -466,6 +481,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
         if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
         if (nt > EMIT_BIG) {
             s_info[tid] = make_uint4(xy, wh, off, cid);
+            if (COARSE) s_fine[tid] = make_uint2(fx0 | (fy0 << 16), fx1 | (fy1 << 16));
             s_big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
         }
 
@@ -484,11 +500,13 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
                     uint32_t q = k / h, r = k - q * h;
                     uint32_t t = (x0 + q) + (y0 + r) * tiles_x;
                     for (uint32_t o = lo; o < hi; o++) {
-                        s_key[o - w0] = t;  // :49 tile index (the high 32 bits of the reference key)
+                        // :49 tile index (the high 32 bits of the reference key); COARSE: block index | tile mask << 16
+                        s_key[o - w0] = COARSE ? (t | (coarse_tile_mask(cs, x0 + q, y0 + r, fx0, fy0, fx1, fy1) << 16)) : t;
                         s_val[o - w0] = cid;
                         t += tiles_x;
                         if (++r == h) {  // next column: y back to y0, x + 1
                             r = 0;
+                            q++;
                             t = t - h * tiles_x + 1;
                         }
                     }
@@ -500,7 +518,13 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
                 const uint32_t lo = max(inf.z, w0), hi = min(inf.z + bnt, w1);
                 for (uint32_t o = lo + tid; o < hi; o += PRE_THREADS) {
                     const uint32_t k = o - inf.z, q = k / bh, r = k - q * bh;
-                    s_key[o - w0] = ((inf.x & 0xffffu) + q) + ((inf.x >> 16) + r) * tiles_x;
+                    const uint32_t bx = (inf.x & 0xffffu) + q, by = (inf.x >> 16) + r;
+                    uint32_t key = bx + by * tiles_x;
+                    if (COARSE) {
+                        const uint2 f = s_fine[s_big[b]];
+                        key |= coarse_tile_mask(cs, bx, by, f.x & 0xffffu, f.x >> 16, f.y & 0xffffu, f.y >> 16) << 16;
+                    }
+                    s_key[o - w0] = key;
                     s_val[o - w0] = inf.w;
                 }
             }
@@ -815,7 +839,8 @@ cudaError_t launch_emit(const EmitParams& p, cudaStream_t s) {
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     if (p.cull) k_emit_cull<<<blocks, PRE_THREADS, 0, s>>>(p);
-    else k_emit<<<blocks, PRE_THREADS, 0, s>>>(p);
+    else if (p.coarse_shift) k_emit<true><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else k_emit<false><<<blocks, PRE_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

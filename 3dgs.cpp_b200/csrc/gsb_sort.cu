@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
     k_onesweep_pass(const KeyT* __restrict__ kin, const uint32_t* __restrict__ vin, KeyT* __restrict__ kout,
                     uint32_t* __restrict__ vout, const uint32_t* __restrict__ d_m, SortCtl* sc, int pass,
                     unsigned long long* status, uint32_t status_tiles, const uint32_t* __restrict__ d_epoch, uint32_t epoch_off,
-                    uint2* __restrict__ ranges) {
+                    uint2* __restrict__ ranges, uint32_t range_mask) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PassSmem<KeyT>& S = *reinterpret_cast<PassSmem<KeyT>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -431,9 +431,10 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
                     for (int it = 0; it < SORT_IPT; it++) {
                         const uint32_t idx = (uint32_t)(it * SORT_THREADS + tid);
                         if (idx < valid) {
-                            const uint32_t key = (uint32_t)k[it];
-                            if (idx == 0 || (uint32_t)sk[idx - 1] != key) atomicMin(&ranges[key].x, (uint32_t)g[it]);
-                            if (idx == valid - 1 || (uint32_t)sk[idx + 1] != key) atomicMin(&ranges[key].y, ~((uint32_t)g[it] + 1u));
+                            // range_mask: the bits that were sorted (a key may carry a payload above them: coarse bins)
+                            const uint32_t key = (uint32_t)k[it] & range_mask;
+                            if (idx == 0 || ((uint32_t)sk[idx - 1] & range_mask) != key) atomicMin(&ranges[key].x, (uint32_t)g[it]);
+                            if (idx == valid - 1 || ((uint32_t)sk[idx + 1] & range_mask) != key) atomicMin(&ranges[key].y, ~((uint32_t)g[it] + 1u));
                         }
                     }
                 }
@@ -489,7 +490,7 @@ cudaError_t launch_sort_t(const SortParams& p, uint32_t P, cudaStream_t s) {
         KeyT* kout = (pass + 1 == P && p.discard_sorted_keys) ? nullptr : keys[dst];
         k_onesweep_pass<KeyT><<<blocks, SORT_THREADS, smem, s>>>(keys[src], p.vals[src], kout, p.vals[dst], p.d_m, p.sc,
                                                                  (int)pass, p.status, p.status_tiles, p.d_epoch, p.epoch_base + pass,
-                                                                 pass + 1 == P ? p.ranges : nullptr);
+                                                                 pass + 1 == P ? p.ranges : nullptr, p.range_key_mask ? p.range_key_mask : 0xffffffffu);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (p.events && (e = cudaEventRecord(p.events[1 + pass], s)) != cudaSuccess) return e;

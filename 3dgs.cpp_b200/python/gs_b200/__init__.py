@@ -314,8 +314,9 @@ class Context:
     def set_debug(self, on=True):
         self._ck(lib.gsb_set_debug(self.h, int(on)))
 
-    def set_tile_cull(self, on=True):
-        self._ck(lib.gsb_set_tile_cull(self.h, int(on)))
+    def set_tile_cull(self, level=1):
+        """gsb_set_tile_cull: 0 reference lists, 1 (True) exact per-tile instance culling, 2 coarse 4x4-tile bins."""
+        self._ck(lib.gsb_set_tile_cull(self.h, int(level)))
 
     def set_timers(self, on=True):
         self._ck(lib.gsb_set_timers(self.h, int(on)))

@@ -147,11 +147,19 @@ uint64_t gsb_scene_size(const gsb_ctx *ctx);
 int gsb_set_mode(gsb_ctx *ctx, gsb_mode mode);
 /* debug != 0: keep every intermediate so gsb_debug_download works (extra HBM traffic). */
 int gsb_set_debug(gsb_ctx *ctx, int debug);
-/* Exact instance culling (default off).  When on, a (Gaussian, tile) instance is dropped at key emission if the
- * Gaussian provably stays below the shader's own alpha < 1/255 cut on every pixel of the tile: the image is
- * bit-identical, but M and the key / payload / tile-range buffers are a subset of the reference's
- * (preprocess_sort.comp:47-58 emits the whole AABB).  Trades a per-candidate test for fewer instances to sort. */
-int gsb_set_tile_cull(gsb_ctx *ctx, int enabled);
+/* How the per-tile lists are produced (default 0).  The IMAGE is bit-identical at every level.
+ *   0  reference-equivalent: one (Gaussian, tile) instance per tile of the AABB (preprocess_sort.comp:47-58); M, keys,
+ *      payloads and tile ranges equal the reference's.
+ *   1  exact instance culling: an instance is dropped at key emission if the Gaussian provably stays below the shader's
+ *      own alpha < 1/255 cut on every pixel of the tile; M and the key / payload / tile-range buffers are an ordered
+ *      subset of the reference's.  Trades a per-candidate test for fewer instances to sort.
+ *   2  coarse bins: the instance sort runs over blocks of 4 x 4 tiles (one entry per (Gaussian, block), the key carrying
+ *      the mask of the block's tiles inside the Gaussian's tile AABB); every tile then walks its block's depth-ordered
+ *      list and keeps the entries whose mask has its bit -- exactly the tile's own list of level 0, in the same order.
+ *      ~3x fewer instances to emit and sort.  num_instances then counts (Gaussian, block) entries; num_instances_aabb
+ *      stays the reference's count.  Unavailable (falls back to 1) with gsb_set_debug, whose downloads are per tile,
+ *      and for frames of more than 65536 blocks. */
+int gsb_set_tile_cull(gsb_ctx *ctx, int level);
 /* per-stage cudaEvent timers (the QueryManager analogue, Renderer.cpp:85-100). Default on. */
 int gsb_set_timers(gsb_ctx *ctx, int enabled);
 /* Replay the camera-independent middle of the frame (both sorts + key emission) from a captured CUDA graph instead of

@@ -109,6 +109,14 @@ def test_fullsize_properties(gs, scene):
         assert np.array_equal(img_c, img)
         assert st_c.num_instances_aabb == M and st_c.num_instances < M
         del img_c
+        # coarse 4x4-tile bins: same pixels again, with direct launches and from the captured graph
+        c.set_tile_cull(2)
+        for timers in (True, False, False):
+            c.set_timers(timers)
+            assert np.array_equal(c.render(u, gs.FORMAT_RGBA32F), img), timers
+        c.set_timers(True)
+        assert c.stats().num_instances_aabb == M and c.stats().num_instances < st_c.num_instances
+        c.set_tile_cull(True)
         # packed swapchain format == quantised float image (through the banded host-output path)
         bgra = c.render(u, gs.FORMAT_BGRA8)
         q = np.rint(np.clip(img[..., [2, 1, 0, 3]], 0, 1) * np.float32(255.0)).astype(np.uint8)
@@ -133,7 +141,7 @@ def test_fullsize_bands_match_oracle(gs, oracle, scene):
         m1, ref1, _ = oracle_band(oracle, vtx, cov, u, rows, 1)
         _, ref0, near_step = oracle_band(oracle, vtx, cov, u, rows, 0)
         assert near_step.mean() < 0.05
-        for cull in (False, True):
+        for cull in (0, 1, 2):
             c.set_tile_cull(cull)
             try:
                 band = c.render(u, gs.FORMAT_RGBA32F, rows=rows)

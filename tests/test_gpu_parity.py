@@ -216,6 +216,39 @@ def test_tile_cull_keeps_the_image_bit_exact(gs, oracle, ctx, cam):
         ctx.set_debug(False)
 
 
+@pytest.mark.parametrize("cam", ["c1", "inside", "odd_size", "wide", "tiny", "away"])
+def test_coarse_bins_keep_the_image_bit_exact(gs, oracle, ctx, cam, monkeypatch):
+    """gsb_set_tile_cull level 2: the instance sort runs over blocks of 4x4 (or 2x2) tiles, the key carries the mask of the
+    block's tiles inside the Gaussian's tile AABB, and every tile keeps the entries with its bit while walking the block's
+    list.  The image must equal the oracle's bit for bit in every format, with timers (direct launches) and without (graph
+    replay), and the instance count must be the number of (Gaussian, block) pairs of the oracle's AABBs."""
+    _, vtx, _ = scenes.c1()
+    u = scenes.camera(cam)
+    ref = oracle_frame(oracle, vtx, u, 1)
+    for shift in ("2", "1"):
+        monkeypatch.setenv("GSB_COARSE_SHIFT", shift)
+        c = gs.Context(0)
+        try:
+            c.set_mode(gs.MODE_EXACT)
+            c.set_tile_cull(2)
+            c.upload(vtx)
+            for timers in (True, False, False):
+                c.set_timers(timers)
+                assert np.array_equal(c.render(u, gs.FORMAT_RGBA32F), ref["rgba"]), (cam, shift, timers)
+            c.set_timers(True)
+            assert np.array_equal(c.render(u, gs.FORMAT_BGRA8), oracle.pack_unorm8(ref["rgba"], bgra=True)), (cam, shift)
+            st = c.stats()
+            a = ref["attr"]["aabb"].astype(np.int64)
+            live = (a[:, 2] > a[:, 0]) & (a[:, 3] > a[:, 1])
+            s = int(shift)
+            blocks = ((((a[:, 2] - 1) >> s) - (a[:, 0] >> s) + 1) * (((a[:, 3] - 1) >> s) - (a[:, 1] >> s) + 1))[live].sum()
+            assert st.num_instances == blocks and st.num_instances_aabb == ref["m"], (cam, shift)
+            c.set_mode(gs.MODE_FAST)
+            assert np.abs(c.render(u, gs.FORMAT_RGBA32F) - ref["rgba"]).max() <= 1e-4
+        finally:
+            c.close()
+
+
 def test_device_scan_with_tile_cull(gs, oracle, ctx):
     """With the exact instance cull on, k_emit scans the CULLED per-Gaussian counts: its offsets must partition the
     emitted list exactly (offset[j+1] - offset[j] instances of Gaussian depth_order[j], contiguous, in that order)."""

@@ -59,7 +59,7 @@ def test_sharded_matches_oracle_with_cull_and_fast_paths(gs, oracle):
     g = gs.Group([0, 0, 0, 0])
     try:
         g.upload(vtx)
-        for cull in (False, True):
+        for cull in (0, 1, 2):  # reference lists, exact instance culling, coarse 4x4-tile bins
             for timers in (True, False):  # timers off: the middle of the frame replays from per-parity CUDA graphs
                 for r in range(4):
                     c = g.context(r)
@@ -105,10 +105,11 @@ def test_sharded_full_size_garden(gs):
         c.close()
         c = None
         g.upload(vtx)
-        for r in range(4):
-            g.context(r).set_tile_cull(True)
-        assert np.array_equal(g.render(u, gs.FORMAT_RGBA32F), want)
-        assert np.array_equal(g.render(u, gs.FORMAT_BGRA8), want8)
+        for level in (1, 2):
+            for r in range(4):
+                g.context(r).set_tile_cull(level)
+            assert np.array_equal(g.render(u, gs.FORMAT_RGBA32F), want), level
+            assert np.array_equal(g.render(u, gs.FORMAT_BGRA8), want8), level
     finally:
         if c is not None:
             c.close()
