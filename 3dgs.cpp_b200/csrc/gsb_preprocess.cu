@@ -414,7 +414,6 @@ __device__ __forceinline__ uint32_t coarse_tile_mask(uint32_t cs, uint32_t bx, u
     return (cols * (cs == 2 ? 0x1111u : 0x5u)) & rows;
 }
 
-template <bool COARSE>
 __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ EmitParams P) {
     __shared__ uint32_t s_chunk;
     __shared__ uint32_t s_wnt[PRE_THREADS / 32];
@@ -422,7 +421,6 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
     __shared__ uint32_t s_nbig;
     __shared__ uint32_t s_big[PRE_THREADS];  // lanes of the chunk holding "big" Gaussians
     __shared__ uint4 s_info[PRE_THREADS];    // x0 | y0 << 16, w | h << 16, local offset, compact id
-    __shared__ uint2 s_fine[COARSE ? PRE_THREADS : 1];  // COARSE: the tile AABB (x0 | y0 << 16, x1 | y1 << 16) of the big Gaussians
     __shared__ uint32_t s_key[EMIT_WIN];
     __shared__ uint32_t s_val[EMIT_WIN];
 
@@ -430,7 +428,6 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
     const uint32_t nv = P.ctl->num_visible;
     const uint32_t num_chunks = (nv + PRE_THREADS - 1) / PRE_THREADS;
     const uint32_t tiles_x = P.tiles_x;
-    const uint32_t cs = P.coarse_shift;
 
     while (true) {
         if (tid == 0) {
@@ -443,19 +440,12 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
         const uint32_t j = chunk * PRE_THREADS + tid;
 
         uint32_t nt = 0, cand = 0, cid = 0, xy = 0, wh = 0;
-        uint32_t fx0 = 0, fy0 = 0, fx1 = 0, fy1 = 0;  // COARSE: the tile AABB
         if (j < nv) {
             cid = __ldg(P.sorted_cid + j);
             const float4 q1 = __ldg(P.recs + (size_t)cid * GSB_REC_F4 + 1);
             xy = __float_as_uint(q1.z);
             wh = __float_as_uint(q1.w);
             cand = (wh & 0xffffu) * (wh >> 16);  // tiles of the AABB = the reference's instance count for this Gaussian
-            if (COARSE && cand != 0) {  // emit the 2^cs x 2^cs tile blocks the AABB touches
-                fx0 = xy & 0xffffu, fy0 = xy >> 16, fx1 = fx0 + (wh & 0xffffu), fy1 = fy0 + (wh >> 16);
-                const uint32_t cx0 = fx0 >> cs, cy0 = fy0 >> cs, cx1 = ((fx1 - 1) >> cs) + 1, cy1 = ((fy1 - 1) >> cs) + 1;
-                xy = cx0 | (cy0 << 16);
-                wh = (cx1 - cx0) | ((cy1 - cy0) << 16);
-            }
             nt = (wh & 0xffffu) * (wh >> 16);
         }
         // ---- block scan of the tile counts (prefix_sum.comp's job) ----
@@ -481,7 +471,6 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
         if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
         if (nt > EMIT_BIG) {
             s_info[tid] = make_uint4(xy, wh, off, cid);
-            if (COARSE) s_fine[tid] = make_uint2(fx0 | (fy0 << 16), fx1 | (fy1 << 16));
             s_big[atomicAdd(&s_nbig, 1u)] = (uint32_t)tid;
         }
 
@@ -500,13 +489,11 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
                     uint32_t q = k / h, r = k - q * h;
                     uint32_t t = (x0 + q) + (y0 + r) * tiles_x;
                     for (uint32_t o = lo; o < hi; o++) {
-                        // :49 tile index (the high 32 bits of the reference key); COARSE: block index | tile mask << 16
-                        s_key[o - w0] = COARSE ? (t | (coarse_tile_mask(cs, x0 + q, y0 + r, fx0, fy0, fx1, fy1) << 16)) : t;
+                        s_key[o - w0] = t;  // :49 tile index (the high 32 bits of the reference key)
                         s_val[o - w0] = cid;
                         t += tiles_x;
                         if (++r == h) {  // next column: y back to y0, x + 1
                             r = 0;
-                            q++;
                             t = t - h * tiles_x + 1;
                         }
                     }
@@ -518,13 +505,7 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit(const __grid_constant__ Em
                 const uint32_t lo = max(inf.z, w0), hi = min(inf.z + bnt, w1);
                 for (uint32_t o = lo + tid; o < hi; o += PRE_THREADS) {
                     const uint32_t k = o - inf.z, q = k / bh, r = k - q * bh;
-                    const uint32_t bx = (inf.x & 0xffffu) + q, by = (inf.x >> 16) + r;
-                    uint32_t key = bx + by * tiles_x;
-                    if (COARSE) {
-                        const uint2 f = s_fine[s_big[b]];
-                        key |= coarse_tile_mask(cs, bx, by, f.x & 0xffffu, f.x >> 16, f.y & 0xffffu, f.y >> 16) << 16;
-                    }
-                    s_key[o - w0] = key;
+                    s_key[o - w0] = ((inf.x & 0xffffu) + q) + ((inf.x >> 16) + r) * tiles_x;
                     s_val[o - w0] = inf.w;
                 }
             }
@@ -620,6 +601,174 @@ __device__ __forceinline__ unsigned long long emit_lookback(unsigned long long* 
         if (lane == 0) st_vol(status + chunk, S2_PREFIX | (ex + blk_total));
     }
     return ex;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_emit_coarse -- k_emit for gsb_set_tile_cull level 2: one entry per (Gaussian, block of 2^cs x 2^cs tiles), key =
+// block id | tile mask << 16 (coarse_tile_mask).  Entries per Gaussian are few (2.4 on the bench scene), so the kernel is
+// bound by the latency of the record gather, the look-back and the barriers, not by the expansion: every thread handles
+// EC_IPT consecutive survivors (four independent gathers in flight, a quarter of the chunks / tickets / barriers).
+// ------------------------------------------------------------------------------------------
+constexpr int EC_IPT = 4;
+constexpr int EC_CHUNK = PRE_THREADS * EC_IPT;
+constexpr int EC_MAXBIG = 32;  // block-expanded Gaussians per chunk; more than that (never seen) fall back to the thread loop
+
+__global__ void __launch_bounds__(PRE_THREADS) k_emit_coarse(const __grid_constant__ EmitParams P) {
+    __shared__ uint32_t s_chunk;
+    __shared__ uint32_t s_wnt[PRE_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_nbig;
+    __shared__ uint4 s_info[EC_MAXBIG];  // x0 | y0 << 16 (blocks), w | h << 16 (blocks), local offset, compact id
+    __shared__ uint2 s_fine[EC_MAXBIG];  // the tile AABB (x0 | y0 << 16, x1 | y1 << 16)
+    __shared__ uint32_t s_key[EMIT_WIN];
+    __shared__ uint32_t s_val[EMIT_WIN];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nv = P.ctl->num_visible;
+    const uint32_t num_chunks = (nv + EC_CHUNK - 1) / EC_CHUNK;
+    const uint32_t bins_x = P.tiles_x, cs = P.coarse_shift;
+
+    while (true) {
+        if (tid == 0) {
+            s_chunk = atomicAdd(&P.ctl->emit_ticket, 1u);
+            s_nbig = 0;
+        }
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= num_chunks) break;
+        const uint32_t j0 = chunk * EC_CHUNK + tid * EC_IPT;  // this thread's survivors j0 .. j0 + EC_IPT - 1 (depth order)
+
+        uint32_t cid[EC_IPT], nt[EC_IPT], bxy[EC_IPT], bwh[EC_IPT], f0[EC_IPT], f1[EC_IPT];
+        if (j0 + EC_IPT <= nv) {
+            const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(P.sorted_cid + j0));
+            cid[0] = c4.x, cid[1] = c4.y, cid[2] = c4.z, cid[3] = c4.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < EC_IPT; k++) cid[k] = j0 + k < nv ? __ldg(P.sorted_cid + j0 + k) : 0u;
+        }
+        float4 q1[EC_IPT];
+#pragma unroll
+        for (int k = 0; k < EC_IPT; k++) q1[k] = j0 + k < nv ? __ldg(P.recs + (size_t)cid[k] * GSB_REC_F4 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t cand = 0, mine = 0;
+#pragma unroll
+        for (int k = 0; k < EC_IPT; k++) {
+            const uint32_t xy = __float_as_uint(q1[k].z), wh = __float_as_uint(q1[k].w);
+            const uint32_t c = (wh & 0xffffu) * (wh >> 16);  // tiles of the AABB = the reference's instance count for this Gaussian
+            cand += c;
+            nt[k] = 0, bxy[k] = 0, bwh[k] = 0, f0[k] = 0, f1[k] = 0;
+            if (c != 0) {
+                const uint32_t x0 = xy & 0xffffu, y0 = xy >> 16, x1 = x0 + (wh & 0xffffu), y1 = y0 + (wh >> 16);
+                const uint32_t cx0 = x0 >> cs, cy0 = y0 >> cs, cx1 = ((x1 - 1) >> cs) + 1, cy1 = ((y1 - 1) >> cs) + 1;
+                bxy[k] = cx0 | (cy0 << 16);
+                bwh[k] = (cx1 - cx0) | ((cy1 - cy0) << 16);
+                f0[k] = x0 | (y0 << 16);
+                f1[k] = x1 | (y1 << 16);
+                nt[k] = (cx1 - cx0) * (cy1 - cy0);
+            }
+            mine += nt[k];
+        }
+        // ---- block scan of the entry counts ----
+        uint32_t incl = mine, cand_sum = cand;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand_sum += __shfl_xor_sync(FULL, cand_sum, o);
+        if (lane == 31) s_wnt[warp] = incl;
+        if (lane == 0 && cand_sum) atomicAdd(&P.ctl->candidates_total, (unsigned long long)cand_sum);
+        __syncthreads();
+        uint32_t before = 0, blk_nt = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; w++) {
+            const uint32_t b = s_wnt[w];
+            if (w < warp) before += b;
+            blk_nt += b;
+        }
+        if (tid == 0) st_vol(P.status + chunk, (chunk == 0 ? S2_PREFIX : S2_AGG) | (unsigned long long)blk_nt);
+        uint32_t off[EC_IPT];
+        {
+            uint32_t run = before + (incl - mine);
+#pragma unroll
+            for (int k = 0; k < EC_IPT; k++) {
+                off[k] = run;
+                run += nt[k];
+            }
+        }
+        uint32_t big = 0;  // bit k: item k is expanded by the whole block
+#pragma unroll
+        for (int k = 0; k < EC_IPT; k++) {
+            if (nt[k] > EMIT_BIG) {
+                const uint32_t slot = atomicAdd(&s_nbig, 1u);
+                if (slot < EC_MAXBIG) {
+                    s_info[slot] = make_uint4(bxy[k], bwh[k], off[k], cid[k]);
+                    s_fine[slot] = make_uint2(f0[k], f1[k]);
+                    big |= 1u << k;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nbig = min(s_nbig, (uint32_t)EC_MAXBIG);
+        unsigned long long base = 0;
+
+        for (uint32_t w0 = 0; w0 == 0 || w0 < blk_nt; w0 += EMIT_WIN) {  // at least once: the look-back lives inside
+            const uint32_t w1 = min(blk_nt, w0 + (uint32_t)EMIT_WIN);
+#pragma unroll
+            for (int k = 0; k < EC_IPT; k++) {  // x outer / y inner inside a Gaussian, like preprocess_sort.comp:47-48
+                if (nt[k] == 0 || ((big >> k) & 1u)) continue;
+                const uint32_t lo = max(off[k], w0), hi = min(off[k] + nt[k], w1);
+                if (lo >= hi) continue;
+                const uint32_t x0 = bxy[k] & 0xffffu, y0 = bxy[k] >> 16, h = bwh[k] >> 16;
+                uint32_t e = lo - off[k];
+                uint32_t q = e / h, r = e - q * h;
+                for (uint32_t o = lo; o < hi; o++) {
+                    const uint32_t m = coarse_tile_mask(cs, x0 + q, y0 + r, f0[k] & 0xffffu, f0[k] >> 16, f1[k] & 0xffffu, f1[k] >> 16);
+                    s_key[o - w0] = ((x0 + q) + (y0 + r) * bins_x) | (m << 16);
+                    s_val[o - w0] = cid[k];
+                    if (++r == h) {
+                        r = 0;
+                        q++;
+                    }
+                }
+            }
+            for (uint32_t b = 0; b < nbig; b++) {
+                const uint4 inf = s_info[b];
+                const uint2 f = s_fine[b];
+                const uint32_t bh = inf.y >> 16, bnt = (inf.y & 0xffffu) * bh;
+                const uint32_t lo = max(inf.z, w0), hi = min(inf.z + bnt, w1);
+                for (uint32_t o = lo + tid; o < hi; o += PRE_THREADS) {
+                    const uint32_t e = o - inf.z, q = e / bh, r = e - q * bh;
+                    const uint32_t bx = (inf.x & 0xffffu) + q, by = (inf.x >> 16) + r;
+                    s_key[o - w0] = (bx + by * bins_x) | (coarse_tile_mask(cs, bx, by, f.x & 0xffffu, f.x >> 16, f.y & 0xffffu, f.y >> 16) << 16);
+                    s_val[o - w0] = inf.w;
+                }
+            }
+            if (w0 == 0 && warp == 0) {  // look-back after the first fill: the predecessors' latency overlaps local work
+                const unsigned long long ex = emit_lookback(P.status, chunk, lane, blk_nt);
+                if (lane == 0) {
+                    s_base = ex;
+                    if (chunk == num_chunks - 1) {
+                        const unsigned long long total = ex + blk_nt;
+                        P.ctl->instances_total = total;
+                        P.ctl->num_instances = total > P.capacity ? P.capacity : (uint32_t)total;
+                        P.ctl->overflow = total > P.capacity ? 1u : 0u;
+                        if (total > P.capacity) atomicOr(&P.ctl->overflow_sticky, 1u);  // survives the next frames' k_frame_init
+                    }
+                }
+            }
+            __syncthreads();
+            if (w0 == 0) base = s_base;
+            for (uint32_t i = tid; i < w1 - w0; i += PRE_THREADS) {  // coalesced copy-out
+                const unsigned long long slot = base + w0 + i;
+                if (slot < P.capacity) {
+                    P.keys[slot] = s_key[i];
+                    P.vals[slot] = s_val[i];
+                }
+            }
+            __syncthreads();
+        }
+    }
 }
 
 struct CullGauss {
@@ -839,8 +988,8 @@ cudaError_t launch_emit(const EmitParams& p, cudaStream_t s) {
     if (blocks > cap) blocks = cap;
     if (blocks == 0) blocks = 1;
     if (p.cull) k_emit_cull<<<blocks, PRE_THREADS, 0, s>>>(p);
-    else if (p.coarse_shift) k_emit<true><<<blocks, PRE_THREADS, 0, s>>>(p);
-    else k_emit<false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else if (p.coarse_shift) k_emit_coarse<<<std::max<uint32_t>(1u, std::min<uint32_t>((p.nv_hint + EC_CHUNK - 1) / EC_CHUNK, cap)), PRE_THREADS, 0, s>>>(p);
+    else k_emit<<<blocks, PRE_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
