@@ -74,10 +74,11 @@ int ensure_arena(gsb_ctx* ctx, uint64_t capacity) {
     dev_free(ctx->vals[1]);
     ctx->capacity = 0;
     ctx->alloc_gen++;
-    CK(dev_alloc(&ctx->keys[0], capacity));
-    CK(dev_alloc(&ctx->keys[1], capacity));
-    CK(dev_alloc(&ctx->vals[0], capacity));
-    CK(dev_alloc(&ctx->vals[1], capacity));
+    // + 16 entries: the blend's TMA segments are 16-B granular and may read up to 3 entries past the end of the last run
+    CK(dev_alloc(&ctx->keys[0], capacity + 16));
+    CK(dev_alloc(&ctx->keys[1], capacity + 16));
+    CK(dev_alloc(&ctx->vals[0], capacity + 16));
+    CK(dev_alloc(&ctx->vals[1], capacity + 16));
     int rc = ensure_sort_status(ctx, std::max<uint64_t>(capacity, ctx->n));
     if (rc != GSB_OK) return rc;
     ctx->capacity = capacity;
@@ -387,7 +388,7 @@ int enqueue_blend(gsb_ctx* ctx, const FramePlan& fp, uint32_t b0, uint32_t b1, v
     bp.format = fmt;
     bp.mode = ctx->mode;
     bp.variant = ctx->blend_variant;
-    bp.stats = (ctx->timers || ctx->debug) ? 1 : 0;
+    bp.stats = ctx->debug ? 2 : (ctx->timers ? 1 : 0);  // 2 also counts blend_pixel_hits (a few % of the kernel)
     bp.one = 1.0f;
     bp.ctl = ctx->ctl;
     CK(launch_blend(bp, stream));

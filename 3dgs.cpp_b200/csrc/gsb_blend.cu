@@ -17,6 +17,7 @@
 // (bit-identical to oracle exp-mode 1).  FAST mode: explicit FMA + ex2.approx.
 #include "gsb_cull.cuh"
 #include "gsb_internal.cuh"
+#include "gsb_tma.cuh"
 
 namespace gsb {
 
@@ -358,7 +359,11 @@ __device__ __forceinline__ void lds_2x64(uint32_t addr, u64& a, u64& b) {
 #ifndef GSB_BLEND2_CHECK
 #define GSB_BLEND2_CHECK 8
 #endif
+#ifndef GSB_BLEND_TMA
+#define GSB_BLEND_TMA 1  // coarse bins: list segments staged by TMA bulk copies (0: per-thread __ldg)
+#endif
 constexpr int B2_THREADS = 128;
+constexpr int B2_SEG = 4 * B2_THREADS;  // list entries scanned per batch at most
 constexpr int B2_BATCH = GSB_BLEND2_BATCH;
 constexpr int B2_WARPS = B2_THREADS / 32;
 
@@ -415,6 +420,12 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     __shared__ uint32_t s_cid[COARSE ? B2_BATCH : 1];   // COARSE: compact id and list position of the batch's entries
     __shared__ uint32_t s_eidx[COARSE ? B2_BATCH : 1];
     __shared__ uint32_t s_wc[B2_WARPS];
+#if GSB_BLEND_TMA
+    // COARSE: the next segment of the block's (key, payload) run, fetched by TMA (cp.async.bulk) while the current batch is
+    // gathered and walked: BASELINE north_star's "TMA bulk staging of per-tile Gaussian runs into shared memory"
+    __shared__ alignas(16) uint32_t s_seg[COARSE ? 2 : 1][COARSE ? B2_SEG + 4 : 4];
+    __shared__ unsigned long long s_bar;
+#endif
     __shared__ uint16_t s_list[B2_WARPS][B2_BATCH];  // per warp: shared-window addresses of the records it must visit
     __shared__ uint32_t s_used, s_walked, s_hits;
     static_assert(sizeof(StagedRec2) * B2_BATCH < 65536, "u16 list entries hold shared-window addresses");
@@ -450,12 +461,44 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
 
     const uint32_t tbit = 16u + (((ty & ((1u << cs) - 1u)) << cs) | (tx & ((1u << cs) - 1u)));  // this tile's bit in a coarse key
     uint32_t cursor = range.x;  // COARSE: next list entry to scan
+#if GSB_BLEND_TMA
+    uint32_t seg_a = range.x & ~3u, seg_parity = 0u;
+    bool seg_pending = COARSE && range.x < range.y;  // a bulk copy into s_seg is in flight
+    if (COARSE) {
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+            if (range.x < range.y) {
+                const uint32_t bytes = (((min(range.y, range.x + (uint32_t)B2_SEG) - seg_a) + 3u) & ~3u) * 4u;
+                mbar_expect_tx(&s_bar, 2u * bytes);
+                tma_load(s_seg[0], P.keys + seg_a, bytes, &s_bar);
+                tma_load(s_seg[1], P.vals + seg_a, bytes, &s_bar);
+            }
+        }
+        __syncthreads();  // the barrier object is initialised before anyone waits on it
+    }
+#endif
     for (uint32_t base = range.x; COARSE ? (cursor < range.y) : (base < range.y); base += B2_BATCH) {
         uint32_t cnt;
         if constexpr (COARSE) {
             // ---- fill: scan up to 4 x 128 entries (loads issued together), compact this tile's entries in list order ----
             constexpr int STEPS = 4;
             uint32_t kk[STEPS], vv[STEPS];
+#if GSB_BLEND_TMA
+            mbar_wait(&s_bar, seg_parity);  // the segment that starts at `cursor` (16-B aligned start seg_a <= cursor)
+            seg_parity ^= 1u;
+            seg_pending = false;
+#pragma unroll
+            for (int j = 0; j < STEPS; j++) {
+                const uint32_t e = cursor + (uint32_t)(j * B2_THREADS + tid);
+                kk[j] = 0u;
+                vv[j] = 0u;
+                if (e < range.y) {
+                    kk[j] = s_seg[0][e - seg_a];
+                    vv[j] = s_seg[1][e - seg_a];
+                }
+            }
+#else
 #pragma unroll
             for (int j = 0; j < STEPS; j++) {
                 const uint32_t e = cursor + (uint32_t)(j * B2_THREADS + tid);
@@ -466,6 +509,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
                     vv[j] = __ldg(P.vals + e);
                 }
             }
+#endif
             uint32_t nfill = 0, steps = 0;
 #pragma unroll
             for (int j = 0; j < STEPS; j++) {
@@ -491,6 +535,21 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             }
             cursor = min(range.y, cursor + steps * (uint32_t)B2_THREADS);
             cnt = nfill;
+#if GSB_BLEND_TMA
+            // every thread has read its entries (the barriers of the steps above): fetch the next segment now, it lands while
+            // this batch's records are gathered and walked
+            if (cursor < range.y) {
+                seg_a = cursor & ~3u;
+                seg_pending = true;
+                if (tid == 0) {
+                    const uint32_t bytes = (((min(range.y, cursor + (uint32_t)B2_SEG) - seg_a) + 3u) & ~3u) * 4u;
+                    fence_proxy_async();
+                    mbar_expect_tx(&s_bar, 2u * bytes);
+                    tma_load(s_seg[0], P.keys + seg_a, bytes, &s_bar);
+                    tma_load(s_seg[1], P.vals + seg_a, bytes, &s_bar);
+                }
+            }
+#endif
         } else {
             cnt = min((uint32_t)B2_BATCH, range.y - base);
         }
@@ -576,7 +635,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
                     if (STATS) {
                         const uint32_t u = base_off + __float_as_uint(idxf) + 1u;
                         used = ((in0k && !ok0 && T0 != 0.0f) || (in1k && !ok1 && T1 != 0.0f)) ? max(used, u) : used;
-                        hits += (in0k && T0 != 0.0f ? 1u : 0u) + (in1k && T1 != 0.0f ? 1u : 0u);
+                        if (P.stats > 1) hits += (in0k && T0 != 0.0f ? 1u : 0u) + (in1k && T1 != 0.0f ? 1u : 0u);  // debug frames only
                     }
 #if GSB_BLEND2_PRED
                     // predicated scalar accumulates (FMA pipe) instead of packed adds + selects (the half-rate ALU pipe is
@@ -635,6 +694,9 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
         if (__syncthreads_and(B2_DONE)) break;
     }
 #undef B2_DONE
+#if GSB_BLEND_TMA
+    if (COARSE && seg_pending) mbar_wait(&s_bar, seg_parity);  // never leave with a bulk copy still writing this CTA's shared memory
+#endif
 
     if (STATS) {
         if (in0 || in1) atomicMax(&s_used, used);

@@ -11,6 +11,7 @@
 // Gaussians, then 32-bit tile-id keys over the M instances; gsb_sort_pairs exposes the u64 form.
 // No tensor cores: integer/byte work, HBM- and latency-bound.
 #include "gsb_internal.cuh"
+#include "gsb_tma.cuh"
 
 namespace gsb {
 
@@ -163,31 +164,6 @@ __device__ __forceinline__ unsigned match_digit8(uint32_t d) {
     return m;
 }
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // exclusive scan of one value per thread across the block (NW warps)
 template <int NW>
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_sums) {
@@ -231,7 +207,7 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
         const uint32_t t = atomicAdd(&sc->ticket[pass], 1u);
         S.tile[buf] = t;
         if (t < num_tiles && m - t * SORT_TILE >= (uint32_t)SORT_TILE) {  // full tile: TMA; the ragged last tile is loaded by the threads
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy accesses to `buf` are done (barrier) -> async proxy may write
+            fence_proxy_async();  // generic-proxy accesses to `buf` are done (barrier) -> async proxy may write
             mbar_expect_tx(&S.mbar[buf], SORT_TILE * (sizeof(KeyT) + 4));
             tma_load(S.keys[buf], kin + (size_t)t * SORT_TILE, SORT_TILE * sizeof(KeyT), &S.mbar[buf]);
             tma_load(S.vals[buf], vin + (size_t)t * SORT_TILE, SORT_TILE * 4, &S.mbar[buf]);
@@ -241,7 +217,7 @@ __global__ void __launch_bounds__(SORT_THREADS, ctas_per_sm<KeyT>())
     if (tid == 0) {
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     // exclusive prefix of the global histogram of this digit (thread d <-> bin d)
     {

@@ -372,6 +372,14 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         vis_acc.append(s.num_visible)
         passes = s.sort_passes
         pass_acc.append(d["sort_pass_ms"])
+    lane_util = None
+    if not sharded:  # blend_pixel_hits is counted on debug frames only
+        ctx.set_debug(True)
+        frame(0, sync=True)
+        sd = ctx.stats()
+        lane_util = sd.blend_pixel_hits / (64.0 * sd.blend_warp_visits) if sd.blend_warp_visits else None
+        ctx.set_debug(False)
+        frame(0, sync=True)
     stage = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     pass_each = [float(x) for x in np.mean(np.array(pass_acc), axis=0)] if pass_acc and pass_acc[0] else []
     M, NV, CONS, VISITS = float(np.mean(m_acc)), float(np.mean(vis_acc)), float(np.mean(cons_acc)), float(np.mean(visit_acc))
@@ -525,7 +533,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         "blend_warp_visits_per_s": VISITS / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
         "blend_pairs_evaluated_per_s": VISITS * 64 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
         # of the evaluated pairs, the fraction that passes render.comp:68-80 (the rest is SIMT lanes riding along)
-        "blend_lane_utilisation": float(np.mean(hit_acc)) / (VISITS * 64) if VISITS > 0 else None,
+        "blend_lane_utilisation": lane_util,
         "blend_records_consumed": CONS, "blend_warp_visits": VISITS,
     }
     if sharded:

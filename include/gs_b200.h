@@ -122,7 +122,8 @@ typedef struct gsb_stats {
     uint64_t blend_warp_visits; /* (warp, record) visits of the blend's inner loop = evaluated pixel-pair x Gaussian work / 64
                                    (each visit evaluates 64 pixels); counted only while timers or debug are on */
     uint64_t blend_pixel_hits;  /* (pixel, Gaussian) pairs of those visits that passed render.comp:68-80 (power <= 0 and
-                                   alpha >= 1/255): hits / (64 * visits) = SIMT lane utilisation of the blend's walk */
+                                   alpha >= 1/255): hits / (64 * visits) = SIMT lane utilisation of the blend's walk; counted on
+                                   gsb_set_debug frames only (0 otherwise) */
     float shard_blend_ms;       /* frame sharding only: this rank's blend kernel alone (render_ms also holds the wait below) */
     float shard_wait_ms;        /* frame sharding only: from the end of this rank's blend until every rank's band has landed */
 } gsb_stats;
