@@ -1,11 +1,14 @@
 // gs_viewer_headless -- the reference viewer's command line (apps/viewer/main.cpp:12-98) without a window:
 //   gs_viewer_headless [-d DEVICE] [-w WIDTH] [-h HEIGHT] [-v] [--frames N] [--camera x,y,z[,qw,qx,qy,qz]]
-//                      [--fov DEG] [--camera-path poses.txt] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply
+//                      [--fov DEG] [--camera-path poses.txt] [--mode exact|fast] [--cull [LEVEL]] [--out image.ppm]
+//                      [--float-out image.pfm] scene.ply
 // --camera-path: one pose per line `x y z qw qx qy qz [fov]` (# comments); `--frames` frames are rendered at each pose
 // and one JSON line is printed per pose (record M for every timed camera).
 // Loads the .ply through GSScene, renders N frames through Renderer::draw() (B8G8R8A8 like the swapchain),
 // prints the six per-stage timers + `instances` (Renderer.cpp:85-100,540) as one JSON line per run and
-// optionally writes the last frame as a binary PPM.  Environment: VKGS_PHYSICAL_DEVICE like the viewer.
+// optionally writes the last frame as a binary PPM (8-bit, what the swapchain would show) and / or as a PFM (float32 RGB, the
+// unquantised blend render.comp:98 stores: what the 1e-4 parity tolerance is defined on).  The first JSON line also carries
+// the load times (file read + activation, upload + cov3D ingest).  Environment: VKGS_PHYSICAL_DEVICE like the viewer.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -19,12 +22,14 @@
 
 static void usage() {
     std::puts("usage: gs_viewer_headless [-d device] [-w width] [-h height] [-v] [--frames n] [--camera x,y,z[,qw,qx,qy,qz]]\n"
-              "                          [--fov deg] [--camera-path poses.txt] [--mode exact|fast] [--cull] [--out image.ppm] scene.ply");
+              "                          [--fov deg] [--camera-path poses.txt] [--mode exact|fast] [--cull [0|1|2]] [--out image.ppm]\n"
+              "                          [--float-out image.pfm] scene.ply");
 }
 
 int main(int argc, char** argv) {
     Renderer::Configuration cfg;
-    std::string out_path, scene, path_file;
+    std::string out_path, float_path, scene, path_file;
+    int cull_level = 0;
     uint32_t frames = 1;
     bool verbose = false, cull = false;
     float cam[7] = {0, 0, 0, 1, 0, 0, 0};
@@ -46,7 +51,11 @@ int main(int argc, char** argv) {
         else if (a == "--frames") frames = static_cast<uint32_t>(std::atoi(next()));
         else if (a == "--fov") fov = static_cast<float>(std::atof(next()));
         else if (a == "--mode") cfg.mode = std::string(next()) == "fast" ? GSB_MODE_FAST : GSB_MODE_EXACT;
-        else if (a == "--cull") cull = true;
+        else if (a == "--cull") {
+            cull = true;
+            cull_level = 1;
+            if (i + 1 < argc && std::strlen(argv[i + 1]) == 1 && argv[i + 1][0] >= '0' && argv[i + 1][0] <= '2') cull_level = argv[++i][0] - '0';
+        } else if (a == "--float-out") float_path = next();
         else if (a == "--out") out_path = next();
         else if (a == "--camera-path") path_file = next();
         else if (a == "--camera") {
@@ -67,7 +76,7 @@ int main(int argc, char** argv) {
         const auto t0 = std::chrono::steady_clock::now();
         renderer.initialize();
         const double load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (cull && gsb_set_tile_cull(renderer.context(), 1) != GSB_OK) throw std::runtime_error("gsb_set_tile_cull failed");
+        if (cull && gsb_set_tile_cull(renderer.context(), cull_level) != GSB_OK) throw std::runtime_error("gsb_set_tile_cull failed");
         struct Pose {
             float v[7];
             float fov;
@@ -98,10 +107,12 @@ int main(int argc, char** argv) {
             renderer.run(frames);
             const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
             const gsb_stats s = renderer.retrieveTimestamps();
-            std::printf("{\"scene\": \"%s\", \"pose\": %zu, \"gaussians\": %llu, \"width\": %u, \"height\": %u, \"frames\": %u, \"fps_wall\": %.2f, "
+            std::printf("{\"scene\": \"%s\", \"pose\": %zu, \"gaussians\": %llu, \"load_ms\": %.1f, \"read_activate_ms\": %.1f, \"upload_ms\": %.1f, "
+                        "\"width\": %u, \"height\": %u, \"frames\": %u, \"fps_wall\": %.2f, "
                         "\"instances\": %llu, \"instances_aabb\": %llu, \"visible\": %llu, \"preprocess_ms\": %.4f, \"prefix_sum_ms\": %.4f, "
                         "\"preprocess_sort_ms\": %.4f, \"sort_ms\": %.4f, \"tile_boundary_ms\": %.4f, \"render_ms\": %.4f, \"frame_ms\": %.4f}\n",
-                        scene.c_str(), pi, (unsigned long long)s.num_gaussians, cfg.width, cfg.height, frames, 1000.0 * frames / wall_ms,
+                        scene.c_str(), pi, (unsigned long long)s.num_gaussians, load_ms, renderer.getScene()->lastReadMs,
+                        renderer.getScene()->lastUploadMs, cfg.width, cfg.height, frames, 1000.0 * frames / wall_ms,
                         (unsigned long long)s.num_instances, (unsigned long long)s.num_instances_aabb, (unsigned long long)s.num_visible,
                         s.preprocess_ms, s.prefix_sum_ms, s.preprocess_sort_ms, s.sort_ms, s.tile_boundary_ms, s.render_ms, s.frame_ms);
         }
@@ -116,6 +127,17 @@ int main(int argc, char** argv) {
                 rgb[p * 3 + 2] = px[p * 4 + 0];
             }
             f.write(reinterpret_cast<const char*>(rgb.data()), static_cast<std::streamsize>(rgb.size()));
+        }
+        if (!float_path.empty()) {  // PFM: "PF", width height, -1.0 (little endian), rows bottom to top, float32 RGB
+            const float* px = static_cast<const float*>(renderer.render(cfg.width, cfg.height, GSB_FORMAT_RGBA32F));
+            std::ofstream f(float_path, std::ios::binary);
+            f << "PF\n" << cfg.width << " " << cfg.height << "\n-1.0\n";
+            std::vector<float> row(static_cast<size_t>(cfg.width) * 3);
+            for (uint32_t y = cfg.height; y-- > 0;) {
+                for (uint32_t x = 0; x < cfg.width; x++)
+                    for (int c = 0; c < 3; c++) row[x * 3 + c] = px[(static_cast<size_t>(y) * cfg.width + x) * 4 + c];
+                f.write(reinterpret_cast<const char*>(row.data()), static_cast<std::streamsize>(row.size() * sizeof(float)));
+            }
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "critical: %s\n", e.what());

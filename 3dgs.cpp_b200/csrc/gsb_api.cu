@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "gsb_ctx.cuh"
@@ -589,31 +590,68 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
         CK(dev_alloc(&ctx->dbg_aabb, n));
         CK(dev_alloc(&ctx->dbg_offsets, n));
     }
-    // stream the AoS records through a bounded staging buffer (C5: 50 M x 240 B = 12 GB on the host)
-    const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), 1u << 20);
-    float* staging = nullptr;
-    if (mem == GSB_MEM_HOST) CK(dev_alloc(&staging, chunk * 60));
-    for (uint64_t off = 0; off < n; off += chunk) {
-        const uint64_t cnt = std::min(chunk, n - off);
-        const float* src = vertices + off * 60;
-        if (mem == GSB_MEM_HOST) {
-            cudaError_t e = cudaMemcpyAsync(staging, src, cnt * 60 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) {
-                cudaFree(staging);
-                return fail(ctx, GSB_ERR_CUDA, "scene H2D copy", e);
+    // Stream the AoS records to the device in chunks (C5: 50 M x 240 B = 12 GB on the host) through a ring of two page-locked
+    // host buffers + two device staging buffers: while chunk k is copied (cudaMemcpyAsync from pinned memory: DMA at PCIe
+    // speed) and ingested by k_ingest_cov3d, the host threads copy chunk k + 1 out of the caller's pageable memory into the
+    // other pinned buffer.  A caller buffer that is already page-locked (gsb_host_alloc / cudaHostRegister) is DMA'd directly.
+    // Replaces vertexBuffer->uploadFrom + GSScene::precomputeCov3D (GSScene.cpp:61,157-184).
+    if (mem == GSB_MEM_DEVICE) {
+        const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(n, 1), 1u << 20);
+        for (uint64_t off = 0; off < n; off += chunk) {
+            const uint64_t cnt = std::min(chunk, n - off);
+            // scale_factor = 1.0f: GSScene.cpp:176
+            cudaError_t e = launch_cov3d(vertices + off * 60, cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream);
+            if (e != cudaSuccess) return fail(ctx, GSB_ERR_CUDA, "cov3d precompute", e);
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else if (n) {
+        cudaPointerAttributes pa{};
+        const bool caller_pinned = cudaPointerGetAttributes(&pa, vertices) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const uint64_t chunk = std::min<uint64_t>(n, 1u << 18);  // 256 K vertices = 63 MB per ring slot
+        float* dev_stage[2] = {nullptr, nullptr};
+        float* pin_stage[2] = {nullptr, nullptr};
+        cudaEvent_t slot_free[2] = {nullptr, nullptr};
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+            e = dev_alloc(&dev_stage[k], chunk * 60);
+            if (e == cudaSuccess && !caller_pinned) e = cudaMallocHost(reinterpret_cast<void**>(&pin_stage[k]), chunk * 60 * sizeof(float));
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&slot_free[k], cudaEventDisableTiming);
+        }
+        const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 8u));
+        uint64_t idx = 0;
+        for (uint64_t off = 0; off < n && e == cudaSuccess; off += chunk, idx++) {
+            const int k = (int)(idx & 1);
+            const uint64_t cnt = std::min(chunk, n - off);
+            const float* src = vertices + off * 60;
+            if (idx >= 2) e = cudaEventSynchronize(slot_free[k]);  // the slot's previous copy + ingest are done
+            if (e != cudaSuccess) break;
+            if (!caller_pinned) {  // pageable -> pinned by a few host threads (one memcpy thread tops out well below PCIe 5)
+                const size_t bytes = cnt * 60 * sizeof(float);
+                const unsigned nt = bytes >= (8u << 20) ? hw : 1u;
+                std::vector<std::thread> pool;
+                const size_t per = (bytes / nt + 63) & ~size_t(63);
+                for (unsigned t = 1; t < nt; t++) {
+                    const size_t b = std::min(bytes, t * per), en = std::min(bytes, b + per);
+                    if (b < en) pool.emplace_back([=] { memcpy(reinterpret_cast<char*>(pin_stage[k]) + b, reinterpret_cast<const char*>(src) + b, en - b); });
+                }
+                memcpy(pin_stage[k], src, std::min(bytes, per));
+                for (auto& th : pool) th.join();
+                src = pin_stage[k];
             }
-            src = staging;
+            e = cudaMemcpyAsync(dev_stage[k], src, cnt * 60 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = launch_cov3d(dev_stage[k], cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(slot_free[k], ctx->stream);
         }
-        // scale_factor = 1.0f: GSScene.cpp:176
-        cudaError_t e = launch_cov3d(src, cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream);
-        if (e == cudaSuccess && mem == GSB_MEM_HOST) e = cudaStreamSynchronize(ctx->stream);  // staging reuse
-        if (e != cudaSuccess) {
-            if (staging) cudaFree(staging);
-            return fail(ctx, GSB_ERR_CUDA, "cov3d precompute", e);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        else cudaStreamSynchronize(ctx->stream);
+        for (int k = 0; k < 2; k++) {
+            if (dev_stage[k]) cudaFree(dev_stage[k]);
+            if (pin_stage[k]) cudaFreeHost(pin_stage[k]);
+            if (slot_free[k]) cudaEventDestroy(slot_free[k]);
         }
+        if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? GSB_ERR_OOM : GSB_ERR_CUDA, "scene upload", e);
     }
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (staging) cudaFree(staging);
     ctx->n = n;
     ctx->m_hint = 0;
     ctx->nv_hint = 0;
@@ -784,6 +822,7 @@ int gsb_get_stats(gsb_ctx* ctx, gsb_stats* out) {
     out->blend_consumed = c->blend_consumed;
     out->blend_warp_visits = c->blend_walked;
     out->blend_pixel_hits = c->blend_hits;
+    out->blend_staged = c->blend_staged;
     out->instance_capacity = ctx->capacity;
     out->sort_passes = ctx->last_passes;
     out->sort_depth_passes = ctx->last_depth_passes;

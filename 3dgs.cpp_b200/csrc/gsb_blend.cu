@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
     // transmittance (0 = finished or outside the image) and colour a/b/c of pixel 0/1
     float T0 = in0 ? 1.0f : 0.0f, T1 = in1 ? 1.0f : 0.0f, ca0 = 0.f, ca1 = 0.f, cb0 = 0.f, cb1 = 0.f, cc0 = 0.f, cc1 = 0.f;
 #define B2_DONE (T0 == 0.0f && T1 == 0.0f)
-    uint32_t used = 0, walked = 0, hits = 0;
+    uint32_t used = 0, walked = 0, hits = 0, staged = 0;
     const uint32_t rec_sh = (uint32_t)__cvta_generic_to_shared(&s_rec[0]);
     const uint32_t list_sh = (uint32_t)__cvta_generic_to_shared(&s_list[warp][0]);
 
@@ -485,7 +485,10 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             constexpr int STEPS = 4;
             uint32_t kk[STEPS], vv[STEPS];
 #if GSB_BLEND_TMA
-            mbar_wait(&s_bar, seg_parity);  // the segment that starts at `cursor` (16-B aligned start seg_a <= cursor)
+            // the segment that starts at `cursor` (16-B aligned start seg_a <= cursor).  One warp polls the mbarrier, the others
+            // sleep on the hardware barrier: 128 threads spinning on try_wait cost issue slots the other CTAs' walks need
+            if (warp == 0) mbar_wait(&s_bar, seg_parity);
+            __syncthreads();
             seg_parity ^= 1u;
             seg_pending = false;
 #pragma unroll
@@ -553,6 +556,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
         } else {
             cnt = min((uint32_t)B2_BATCH, range.y - base);
         }
+        if (STATS) staged += cnt;
 #pragma unroll
         for (int j = 0; j < B2_BATCH / B2_THREADS; j++) {
             const uint32_t li = (uint32_t)(j * B2_THREADS + tid);
@@ -752,6 +756,7 @@ __global__ void __launch_bounds__(B2_THREADS, GSB_BLEND2_MIN_BLOCKS) k_blend2(co
             if (s_used) atomicAdd(&P.ctl->blend_consumed, (unsigned long long)s_used);
             if (s_walked) atomicAdd(&P.ctl->blend_walked, (unsigned long long)s_walked);
             if (s_hits) atomicAdd(&P.ctl->blend_hits, (unsigned long long)s_hits);
+            if (staged) atomicAdd(&P.ctl->blend_staged, (unsigned long long)staged);
         }
     }
 }

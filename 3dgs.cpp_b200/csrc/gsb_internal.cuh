@@ -48,6 +48,7 @@ struct Control {
     unsigned long long candidates_total;  // AABB instances before tile culling (the reference's M)
     unsigned long long blend_walked;      // (warp, record) visits of the blend's inner loop (k_blend2 with stats on)
     unsigned long long blend_hits;        // (pixel, Gaussian) pairs of those visits that passed the shader's tests
+    unsigned long long blend_staged;      // records gathered into shared memory by the blend
     SortCtl sort_depth;        // Gaussian-level sort (32-bit depth keys)
     SortCtl sort_tile;         // instance-level sort (tile-id keys); also used by gsb_sort_pairs
     // frame sharding (gsb_shard.cu): k_route's chunk tickets and per-destination-band survivor totals

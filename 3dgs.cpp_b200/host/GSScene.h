@@ -47,6 +47,8 @@ public:
 
     // Parse + activate + upload to `ctx` (replaces load(const std::shared_ptr<VulkanContext>&)).
     void load(gsb_ctx* ctx);
+    // wall-clock of the last load(): file read + activation (loadToHost), and gsb_scene_upload (pinned ring + cov3D ingest)
+    double lastReadMs = 0.0, lastUploadMs = 0.0;
     // Parse + activate only (no device needed); fills `vertices()`.
     void loadToHost();
 

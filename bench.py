@@ -354,7 +354,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         frame(i, sync=True)
 
     # per-stage / per-kernel times (library cudaEvents), sampled on separate untimed frames
-    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc, visit_acc, hit_acc = {}, [], [], [], [], [], [], []
+    stage_acc, m_acc, cons_acc, vis_acc, pass_acc, aabb_acc, visit_acc, staged_acc = {}, [], [], [], [], [], [], []
     passes = 0
     for i in range(NUM_CAMERAS):
         frame(i, sync=True)
@@ -368,7 +368,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         aabb_acc.append(s.num_instances_aabb)
         cons_acc.append(s.blend_consumed)
         visit_acc.append(s.blend_warp_visits)
-        hit_acc.append(s.blend_pixel_hits)
+        staged_acc.append(s.blend_staged)
         vis_acc.append(s.num_visible)
         passes = s.sort_passes
         pass_acc.append(d["sort_pass_ms"])
@@ -383,6 +383,8 @@ def measure(env, wl_name, wl, steps, warmup, headline):
     stage = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     pass_each = [float(x) for x in np.mean(np.array(pass_acc), axis=0)] if pass_acc and pass_acc[0] else []
     M, NV, CONS, VISITS = float(np.mean(m_acc)), float(np.mean(vis_acc)), float(np.mean(cons_acc)), float(np.mean(visit_acc))
+    STAGED = float(np.mean(staged_acc))
+    coarse = int(args.tile_cull) == 2
 
     # ---- value: K frames, device resident, one stream, CUDA events, max over ranks ----
     ctx.set_timers(False)  # from here on the camera-independent middle of the frame replays from a captured CUDA graph
@@ -475,12 +477,15 @@ def measure(env, wl_name, wl, steps, warmup, headline):
     alg = {
         "k_project": n_local * 40 + (nv * 192 + nv * (64 + 8)) * (1.0 if not sharded else 1.0),  # scene read + SH of survivors + 64-B record, depth key + payload
         kd: nv * (4 + 16 * 4 - 4),                                 # histogram read + 4 x (8 B read + 8 B written); the last pass writes no keys
-        "k_emit": nv * (4 + 32) + 8 * M,                           # sorted ids + one 32-B record sector per survivor in, (tile id, payload) out
+        "k_emit": nv * (4 + 32) + 8 * M,                           # sorted ids + one 32-B record sector per survivor in, (tile / block id, payload) out
         "k_sort_hist": 4 * M,
         # per launch, averaged over the passes: 8 B read + 8 B written per (tile id, payload) pair; the last pass
         # writes payloads only (4 B) plus the tile ranges
-        "k_onesweep_pass": (16 * M * passes - 4 * M + 8 * T_tiles) / max(passes, 1),
-        "k_blend": CONS * (4 + 36) + H * W * bpp / world * (world if sharded else 1),
+        # with coarse bins the blend reads the sorted keys (tile masks), so the last pass writes them too
+        "k_onesweep_pass": (16 * M * passes - (0 if coarse else 4 * M) + 8 * T_tiles) / max(passes, 1),
+        # per tile: list entries scanned (coarse bins: 4-B key + 4-B payload each; otherwise the 4-B payload) + 36 B of record
+        # for every entry staged + the tile's pixels
+        "k_blend": (CONS * 8 + STAGED * 36 if coarse else CONS * (4 + 36)) + H * W * bpp / world * (world if sharded else 1),
     }
     dur = {"k_project": stage["preprocess_ms"], kd: stage["sort_depth_ms"], "k_emit": stage["preprocess_sort_ms"],
            "k_sort_hist": stage["sort_hist_ms"], "k_onesweep_pass": stage["sort_pass_ms"],
@@ -534,7 +539,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         "blend_pairs_evaluated_per_s": VISITS * 64 / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
         # of the evaluated pairs, the fraction that passes render.comp:68-80 (the rest is SIMT lanes riding along)
         "blend_lane_utilisation": lane_util,
-        "blend_records_consumed": CONS, "blend_warp_visits": VISITS,
+        "blend_records_consumed": CONS, "blend_records_staged": STAGED, "blend_warp_visits": VISITS,
     }
     if sharded:
         out["per_rank"] = per_rank

@@ -124,6 +124,8 @@ typedef struct gsb_stats {
     uint64_t blend_pixel_hits;  /* (pixel, Gaussian) pairs of those visits that passed render.comp:68-80 (power <= 0 and
                                    alpha >= 1/255): hits / (64 * visits) = SIMT lane utilisation of the blend's walk; counted on
                                    gsb_set_debug frames only (0 otherwise) */
+    uint64_t blend_staged;      /* records gathered into shared memory by the blend (with coarse bins: this tile's entries among the
+                                   blend_consumed list entries it scanned; otherwise equal to the entries read) */
     float shard_blend_ms;       /* frame sharding only: this rank's blend kernel alone (render_ms also holds the wait below) */
     float shard_wait_ms;        /* frame sharding only: from the end of this rank's blend until every rank's band has landed */
 } gsb_stats;

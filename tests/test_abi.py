@@ -32,7 +32,7 @@ def test_abi_version_and_struct_sizes(gs):
     assert gs.lib.gsb_abi_version() == 3
     assert C.sizeof(gs.Uniforms) == 160  # Renderer::UniformBuffer, std140
     assert gs.ATTR_DTYPE.itemsize == 64  # VertexAttribute
-    assert C.sizeof(gs.Stats) == 6 * 8 + 2 * 4 + 7 * 4 + 3 * 4 + 8 * 4 + 2 * 4 + 8 + 8 + 2 * 4
+    assert C.sizeof(gs.Stats) == 6 * 8 + 2 * 4 + 7 * 4 + 3 * 4 + 8 * 4 + 2 * 4 + 8 + 8 + 8 + 2 * 4
 
 
 def test_no_cpu_fallback_without_device(gs):

@@ -41,6 +41,18 @@ def test_headless_viewer_cli(gs, oracle, tmp_path):
     assert data.startswith(head)
     rgb = np.frombuffer(data[len(head):], np.uint8).reshape(480, 640, 3)
     assert np.array_equal(rgb, oracle.pack_unorm8(ref["rgba"])[..., :3])
+    assert info["load_ms"] > 0 and info["read_activate_ms"] > 0 and info["upload_ms"] > 0
+    # float dump (PFM, rows bottom to top) with coarse bins on: the unquantised blend, bit for bit
+    pfm = tmp_path / "frame.pfm"
+    r = subprocess.run([str(exe), "-w", "640", "-h", "480", "--camera", "0,0,5", "--cull", "2", "--float-out", str(pfm), str(ply)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    blob = pfm.read_bytes()
+    head_f = b"PF\n640 480\n-1.0\n"
+    assert blob.startswith(head_f)
+    img = np.frombuffer(blob[len(head_f):], "<f4").reshape(480, 640, 3)[::-1]
+    assert np.array_equal(img, ref["rgba"][..., :3])
+    assert json.loads(r.stdout.strip().splitlines()[-1])["instances_aabb"] == ref["m"]
     # camera path: one JSON line per pose, pose 0 = the camera above, pose 1 looks from further away
     poses = tmp_path / "poses.txt"
     poses.write_text("# x y z qw qx qy qz [fov]\n0 0 5 1 0 0 0\n0 0 7 1 0 0 0 60\n")

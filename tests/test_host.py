@@ -92,6 +92,21 @@ def test_ply_roundtrip_and_both_loaders_agree(gs, oracle, tmp_path):
     assert np.array_equal(a, gs.activate_records(rec))
 
 
+def test_large_ply_is_read_by_several_threads_and_stays_exact(gs, tmp_path):
+    """GSScene::loadToHost splits the body over threads (pread on disjoint slices) once there are more than 65536 records:
+    the result must equal the single-pass activation, record for record, and a file cut inside a later slice is an error."""
+    n = 200_003  # 4 slices, the last one ragged
+    rec = gs.synth_records(7, n)
+    path = tmp_path / "big.ply"
+    gs.write_ply(path, rec)
+    got = gs.load_ply(path)
+    assert got.shape == (n, 60) and np.array_equal(got, gs.activate_records(rec))
+    data = path.read_bytes()
+    path.write_bytes(data[:-5000])
+    with pytest.raises(RuntimeError, match="Unexpected end of file"):
+        gs.load_ply(path)
+
+
 def test_missing_scene_file_raises_like_the_reference(gs):
     with pytest.raises(RuntimeError, match="File does not exist"):
         gs.load_ply("/nonexistent/scene.ply")

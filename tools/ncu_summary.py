@@ -10,7 +10,7 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr, data = rows[0], rows[2:]
 ix = {h: i for i, h in enumerate(hdr)}
 def short(name):
-    for k in ("k_project", "k_emit_cull", "k_emit", "k_sort_hist", "k_onesweep_pass", "k_tile_ranges", "k_blend"):
+    for k in ("k_project", "k_emit_cull", "k_emit_coarse", "k_emit", "k_sort_hist", "k_onesweep_pass", "k_tile_ranges", "k_frame_init", "k_blend2", "k_blend"):
         if k in name:
             return k + ("<u64>" if "IyE" in name or "unsigned long long *, " in name and k == "k_onesweep_pass" and "unsigned long long *, const unsigned int *, unsigned long long" in name else "")
     return name[:30]
@@ -32,7 +32,7 @@ out = [f"# Profile summary {tag}", "",
        "| kernel | ms/launch | launches/frame | algorithmic MB/launch | achieved GB/s | frac of measured 6580 GB/s | share of frame |", "|---|---|---|---|---|---|---|"]
 for k, v in bench["kernels"].items():
     out.append(f"| {k} | {v['ms_per_launch']:.4f} | {v['launches_per_step']} | {v['alg_bytes_per_launch']/1e6:.1f} | {v['achieved_gbs']:.0f} | {v['achieved_gbs']/6580.3:.3f} | {v['share_of_step']:.3f} |")
-out += ["", f"sort keys/s (M / t_sort): {bench['sort_keys_per_s']:.3e}; blend pair-evals/s: {bench['blend_pair_evals_per_s']:.3e}", "",
+out += ["", f"sort keys/s (M / t_sort): {bench['sort_keys_per_s']:.3e}; blend warp visits/s: {bench.get('blend_warp_visits_per_s') or 0:.3e} (one visit = 64 pixel x Gaussian pairs evaluated); lane utilisation {bench.get('blend_lane_utilisation')}", "",
         "## ncu --set full, one frame (cold cache, serialised; compare shares, not absolutes)", "",
         "| kernel | " + " | ".join(c[1] for c in cols) + " |", "|---|" + "---|" * len(cols)]
 for r in data:
