@@ -9,6 +9,23 @@ using namespace gsmath;
 
 Renderer::Renderer(Configuration cfg) : configuration(std::move(cfg)) {}
 
+void Renderer::HostFrame::resize(size_t n) {
+    if (n > capacity) {
+        if (ptr) gsb_host_free(ptr);
+        ptr = nullptr;
+        capacity = 0;
+        void* p = nullptr;
+        if (gsb_host_alloc(&p, n) != GSB_OK) throw std::runtime_error("gsb_host_alloc failed (page-locked frame buffer)");
+        ptr = static_cast<unsigned char*>(p);
+        capacity = n;
+    }
+    bytes = n;
+}
+
+Renderer::HostFrame::~HostFrame() {
+    if (ptr) gsb_host_free(ptr);
+}
+
 Renderer::~Renderer() {
     if (ctx) gsb_destroy(ctx);
 }
