@@ -15,11 +15,12 @@
 //             to the single-GPU frame.  (A separate k_route pass over the compacted records cost 0.1-0.2 ms more.)
 //   k_blend2  stores its band straight into the whole-frame buffer of EVERY rank (the all-gather of the framebuffer,
 //             done by the producer's stores; GSB_SHARD_GATHER=nccl replaces it by one in-place ncclAllGather).
-// Cross-GPU ordering uses mailbox words in peer memory: `started` (a rank entered frame f: its buffers of frame f - 2
-// may be overwritten), `routed` (+ counts: its records for my band have landed), `framed` (+ overflow flag: its band of
-// the framebuffer has landed).  A signal is a one-warp kernel after the producing kernel, a wait a one-warp kernel that
+// Cross-GPU ordering uses mailbox words in peer memory: `routed` (+ counts: a rank's records for my band have landed) and
+// `framed` (+ overflow flag: its band of the framebuffer has landed).  A signal is a one-warp kernel after the producing kernel, a wait a one-warp kernel that
 // spins on acquire loads (bounded: a dead peer raises an error instead of hanging the GPU).  Exchange and frame
-// buffers are double-buffered by frame parity.
+// buffers are double-buffered by frame parity; no "may I overwrite your buffers" handshake is needed: a rank writes into
+// buffers of parity f & 1 in frame f, their last readers ran in frame f - 2, and every rank waited for every rank's
+// `framed` of frame f - 2 (which follows that rank's last read) before it left frame f - 2.
 //
 // Two ways to form the group, same kernels:
 //   gsb_group_create      one process drives all GPUs (SURVEY 8b `gs_create_sharded(int ndev, ...)`); peers are plain
@@ -44,7 +45,7 @@ using namespace gsb;
 namespace gsb {
 
 struct Mailbox {  // in every rank's window; every word has exactly one writer (peer p writes index p)
-    uint32_t started[GSB_MAX_SHARDS];
+    uint32_t reserved[GSB_MAX_SHARDS];
     uint32_t routed[GSB_MAX_SHARDS];
     uint32_t framed[GSB_MAX_SHARDS];
     uint32_t count[2][GSB_MAX_SHARDS];     // [parity][source]: records delivered for my band
@@ -319,12 +320,11 @@ PeerWords words_of(ShardState* sh, size_t field_offset, int index_is_rank, int p
 
 constexpr long long WAIT_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s at 1.9 GHz: a dead peer becomes an error, not a hung GPU
 
-// One sharded frame is enqueued in four phases; a phase ends where the stream would next WAIT for the other ranks:
-//   1  frame start, signal `started`
-//   2  wait `started`, k_project over the local slice (its survivors are stored straight into peer memory), signal `routed`
-//   3  wait `routed`, gather, depth sort / emission / tile sort, blend (peer stores), signal `framed`
-//   4  wait `framed`, mailbox + stats copy, completion event
-// A process that drives ONE rank enqueues 1-4 back to back.  A group that drives every rank from one host thread enqueues
+// One sharded frame is enqueued in three phases; a phase ends where the stream would next WAIT for the other ranks:
+//   1  frame start, k_project over the local slice (its survivors are stored straight into peer memory), signal `routed`
+//   2  wait `routed`, gather, depth sort / emission / tile sort, blend (peer stores), signal `framed`
+//   3  wait `framed`, mailbox + stats copy, completion event
+// A process that drives ONE rank enqueues 1-3 back to back.  A group that drives every rank from one host thread enqueues
 // phase k of EVERY rank before phase k + 1 of any: each wait is then enqueued after all the signals it depends on, so a
 // host-side call that blocks until another device drains (first-use module loading, cudaMalloc / cudaFree with peer
 // mappings) can never sit between a spinning wait and the signal that would release it.  (Measured on 2 x B200:
@@ -365,15 +365,8 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
         CK(launch_frame_init(ctx->ctl, ctx->project_status, std::max(chunks_local, 1u), sh->emit_status_d, std::max(chunks_cap, 1u), ctx->ranges,
                              F.fp.T, stream, sh->route_status, std::max(chunks_local, 1u) * GSB_MAX_SHARDS));
         if (ctx->timers) CK(cudaEventRecord(ctx->ev[0], stream));
-        // S1: I have entered frame f (my buffers of parity f & 1 -- last used by frame f - 2 -- may be overwritten)
-        k_shard_signal<<<1, 32, 0, stream>>>(words_of(sh, offsetof(Mailbox, started), 1, 0), F.f, G, PeerWords{}, nullptr, 0);
-        CK(cudaGetLastError());
-        return GSB_OK;
-    }
-    if (phase == 2) {
-        // ---- wait until every rank has entered the frame, then k_project over the local slice (whole frame, no band clip)
-        // delivers every survivor straight into the exchange buffers of the ranks whose band it touches, and announces it ----
-        k_shard_wait<<<1, 32, 0, stream>>>(mb->started, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
+        // ---- k_project over the local slice (whole frame, no band clip) delivers every survivor straight into the exchange
+        // buffers (parity f & 1: last read in frame f - 2, see the header) of the ranks whose band it touches, and announces it ----
         ProjectParams pp{};
         pp.pos_op = ctx->pos_op;
         pp.cov_a = ctx->cov_a;
@@ -402,7 +395,7 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
         CK(cudaGetLastError());
         return GSB_OK;
     }
-    if (phase == 3) {
+    if (phase == 2) {
         k_shard_wait<<<1, 32, 0, stream>>>(mb->routed, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
         if (ctx->timers) CK(cudaEventRecord(ctx->ev[1], stream));  // "preprocess" = projection + exchange
         GatherParams gp{};
@@ -467,7 +460,7 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
         CK(cudaGetLastError());
         return GSB_OK;
     }
-    // phase 4: wait for everyone's band
+    // phase 3: wait for everyone's band
     k_shard_wait<<<1, 32, 0, stream>>>(mb->framed, F.f, G, &mb->error, WAIT_TIMEOUT_CYCLES);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(sh->mailbox_host, mb, sizeof(Mailbox), cudaMemcpyDeviceToHost, stream));
@@ -480,7 +473,7 @@ int enqueue_sharded(gsb_ctx* ctx, const gsb_uniforms* ubo, int fmt, cudaStream_t
     F.ubo = *ubo;
     F.fmt = fmt;
     F.stream = stream;
-    for (int phase = 1; phase <= 4; phase++) {
+    for (int phase = 1; phase <= 3; phase++) {
         int rc = enqueue_sharded_phase(ctx, F, phase);
         if (rc != GSB_OK) return rc;
     }
@@ -865,7 +858,7 @@ static int group_enqueue(gsb_group* g, const gsb_uniforms* ubo, int fmt) {
         F[i].stream = c->stream;
     }
     // one host thread enqueues every rank's frame, phase by phase (see enqueue_sharded_phase); the ranks meet on the device
-    for (int phase = 1; phase <= 4; phase++)
+    for (int phase = 1; phase <= 3; phase++)
         for (size_t i = 0; i < g->ctx.size(); i++) {
             gsb_ctx* c = g->ctx[i];
             cudaSetDevice(c->device);

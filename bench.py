@@ -525,8 +525,8 @@ def measure(env, wl_name, wl, steps, warmup, headline):
                              else "gsb_render(host UBO -> pinned host BGRA8 frame: the blend stores straight into host memory), one blocking call per frame")},
         # k_frame_init, k_project, hist + 4 passes (depth), k_emit, hist + P passes (tile; the last one also writes the tile
         # ranges), k_blend -- the sorts and the emission are launched through one captured CUDA graph per frame; sharded
-        # frames add k_shard_gather and 3 signal + 3 wait one-warp kernels (the survivor routing is inside k_project)
-        "gpu_launches": int((10 + passes + (7 if sharded else 0)) * steps),
+        # frames add k_shard_gather and 2 signal + 2 wait one-warp kernels (the survivor routing is inside k_project)
+        "gpu_launches": int((10 + passes + (5 if sharded else 0)) * steps),
         "clocks": clocks,
         "roofline": roof,
         "kernels": kern,
