@@ -342,6 +342,7 @@ static int enqueue_front(gsb_ctx* ctx, const gsb_uniforms* ubo, uint32_t rb, uin
     pp.cov_a = ctx->cov_a;
     pp.cov_b = ctx->cov_b;
     pp.sh = ctx->sh;
+    pp.sh_half = ctx->scene_sh_half ? 1 : 0;
     pp.n = n;
     pp.index_base = 0;
     pp.ubo = *ubo;
@@ -577,7 +578,8 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
     CK(dev_alloc(&ctx->pos_op, n));
     CK(dev_alloc(&ctx->cov_a, n));
     CK(dev_alloc(&ctx->cov_b, n));
-    CK(dev_alloc(&ctx->sh, n * 48));
+    ctx->scene_sh_half = ctx->sh_half;
+    CK(dev_alloc(&ctx->sh, n * (ctx->scene_sh_half ? 24 : 48)));
     CK(dev_alloc(&ctx->recs, n * GSB_REC_F4));
     CK(dev_alloc(&ctx->dkeys[0], n));
     CK(dev_alloc(&ctx->dkeys[1], n));
@@ -600,7 +602,7 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
         for (uint64_t off = 0; off < n; off += chunk) {
             const uint64_t cnt = std::min(chunk, n - off);
             // scale_factor = 1.0f: GSScene.cpp:176
-            cudaError_t e = launch_cov3d(vertices + off * 60, cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream);
+            cudaError_t e = launch_cov3d(vertices + off * 60, cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream, ctx->scene_sh_half);
             if (e != cudaSuccess) return fail(ctx, GSB_ERR_CUDA, "cov3d precompute", e);
         }
         CK(cudaStreamSynchronize(ctx->stream));
@@ -640,7 +642,7 @@ int gsb_scene_upload(gsb_ctx* ctx, const float* vertices, uint64_t n, gsb_memory
                 src = pin_stage[k];
             }
             e = cudaMemcpyAsync(dev_stage[k], src, cnt * 60 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) e = launch_cov3d(dev_stage[k], cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream);
+            if (e == cudaSuccess) e = launch_cov3d(dev_stage[k], cnt, off, ctx->pos_op, ctx->cov_a, ctx->cov_b, ctx->sh, 1.0f, ctx->stream, ctx->scene_sh_half);
             if (e == cudaSuccess) e = cudaEventRecord(slot_free[k], ctx->stream);
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -672,6 +674,12 @@ uint64_t gsb_scene_size(const gsb_ctx* ctx) { return ctx ? ctx->n : 0; }
 int gsb_set_mode(gsb_ctx* ctx, gsb_mode mode) {
     if (!ctx || (mode != GSB_MODE_EXACT && mode != GSB_MODE_FAST)) return GSB_ERR_INVALID;
     ctx->mode = mode;
+    return GSB_OK;
+}
+
+int gsb_set_sh_storage(gsb_ctx* ctx, int half_precision) {
+    if (!ctx) return GSB_ERR_INVALID;
+    ctx->sh_half = half_precision != 0;  // the next gsb_scene_upload stores the coefficients that way
     return GSB_OK;
 }
 

@@ -39,7 +39,9 @@ struct gsb_ctx {
     float4* pos_op = nullptr;
     float4* cov_a = nullptr;
     float2* cov_b = nullptr;
-    float* sh = nullptr;
+    float* sh = nullptr;        // [n][48] fp32, or [n][48] fp16 when sh_half
+    bool sh_half = false;       // gsb_set_sh_storage(1): takes effect at the next gsb_scene_upload
+    bool scene_sh_half = false; // storage of the uploaded scene
 
     // frame state
     Control* ctl = nullptr;

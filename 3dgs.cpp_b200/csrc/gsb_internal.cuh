@@ -61,6 +61,7 @@ struct ProjectParams {
     const float4* cov_a;
     const float2* cov_b;
     const float* sh;
+    int sh_half;          // sh holds 48 fp16 per Gaussian (gsb_set_sh_storage; non-parity)
     uint32_t n;
     uint32_t index_base;  // global index of this context's first Gaussian (frame sharding: the rank's slice; else 0)
     gsb_uniforms ubo;
@@ -101,7 +102,7 @@ struct EmitParams {
 };
 
 cudaError_t launch_cov3d(const float* vtx_aos, uint64_t count, uint64_t dst_offset, float4* pos_op,
-                         float4* cov_a, float2* cov_b, float* sh, float scale_factor, cudaStream_t s);
+                         float4* cov_a, float2* cov_b, float* sh, float scale_factor, cudaStream_t s, bool sh_half = false);
 cudaError_t launch_project(const ProjectParams& p, bool debug, cudaStream_t s);
 cudaError_t launch_emit(const EmitParams& p, cudaStream_t s);
 

@@ -14,6 +14,8 @@
 //
 // Arithmetic: compiled with -fmad=false; every fp32 operation is a single IEEE op in the order
 // of the GLSL source, so results are value-identical to the oracle (bit-exact parity).
+#include <cuda_fp16.h>
+
 #include "gsb_cull.cuh"
 #include "gsb_internal.cuh"
 
@@ -76,11 +78,23 @@ __device__ __forceinline__ float sh_term(float a, float s, const ShDir& d) {
     else return a + ((SH_C3_6 * s) * d.x) * d.w15;
 }
 
-template <int G>
+template <int G, bool SH16>
 __device__ __forceinline__ void sh_group(const float4* __restrict__ sh4, float (&c)[3], const ShDir& d) {
-    // coefficients 4G .. 4G+3 = floats 12G .. 12G+11 = three float4
-    const float4 t0 = __ldg(sh4 + 3 * G), t1 = __ldg(sh4 + 3 * G + 1), t2 = __ldg(sh4 + 3 * G + 2);
-    const float f[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
+    // coefficients 4G .. 4G+3 = floats 12G .. 12G+11 = three float4 (SH16, non-parity: 12 halves = three 8-B words)
+    float f[12];
+    if constexpr (SH16) {
+        const uint2* sh2 = reinterpret_cast<const uint2*>(sh4);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint2 w = __ldg(sh2 + 3 * G + k);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+            f[4 * k + 0] = lo.x, f[4 * k + 1] = lo.y, f[4 * k + 2] = hi.x, f[4 * k + 3] = hi.y;
+        }
+    } else {
+        const float4 t0 = __ldg(sh4 + 3 * G), t1 = __ldg(sh4 + 3 * G + 1), t2 = __ldg(sh4 + 3 * G + 2);
+        f[0] = t0.x, f[1] = t0.y, f[2] = t0.z, f[3] = t0.w, f[4] = t1.x, f[5] = t1.y, f[6] = t1.z, f[7] = t1.w;
+        f[8] = t2.x, f[9] = t2.y, f[10] = t2.z, f[11] = t2.w;
+    }
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
         c[ch] = sh_term<4 * G + 0>(c[ch], f[0 + ch], d);
@@ -90,7 +104,8 @@ __device__ __forceinline__ void sh_group(const float4* __restrict__ sh4, float (
     }
 }
 
-// preprocess.comp:73-108 compute_sh(); sh = 48 floats RGB-interleaved, as 12 float4.
+// preprocess.comp:73-108 compute_sh(); sh = 48 floats RGB-interleaved, as 12 float4 (SH16: 48 halves).
+template <bool SH16>
 __device__ __forceinline__ void compute_sh(const float4* __restrict__ sh4, float px, float py, float pz,
                                            const float* cam, float& r, float& g, float& b) {
     const float dx = px - cam[0], dy = py - cam[1], dz = pz - cam[2];
@@ -107,10 +122,10 @@ __device__ __forceinline__ void compute_sh(const float4* __restrict__ sh4, float
     d.w12 = ((2.0f * d.z) * d.z - (3.0f * d.x) * d.x) - (3.0f * d.y) * d.y;
     d.w15 = xx - (3.0f * d.y) * d.y;
     float c[3] = {0.f, 0.f, 0.f};
-    sh_group<0>(sh4, c, d);
-    sh_group<1>(sh4, c, d);
-    sh_group<2>(sh4, c, d);
-    sh_group<3>(sh4, c, d);
+    sh_group<0, SH16>(sh4, c, d);
+    sh_group<1, SH16>(sh4, c, d);
+    sh_group<2, SH16>(sh4, c, d);
+    sh_group<3, SH16>(sh4, c, d);
     c[0] = c[0] + 0.5f;
     c[1] = c[1] + 0.5f;
     c[2] = c[2] + 0.5f;
@@ -130,7 +145,7 @@ __device__ __forceinline__ void compute_sh(const float4* __restrict__ sh4, float
 // from registers into the exchange buffer of every rank whose band the AABB touches (stores into peer-mapped memory over
 // NVLink).  Slots are deterministic (Gaussian-index order inside this source's region), so every band's survivor list is
 // ordered exactly like the single-GPU compaction and the band's pixels are bit-identical.
-template <bool DEBUG, bool ROUTED>
+template <bool DEBUG, bool ROUTED, bool SH16>
 __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project(const __grid_constant__ ProjectParams P) {
     __shared__ uint32_t s_chunk;
     __shared__ uint32_t s_wsurv[PRE_THREADS / 32];
@@ -265,7 +280,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
         }
         // ---- SH colour of survivors (overlaps the look-back of other chunks) ----
         float colr = 0.f, colg = 0.f, colb = 0.f;
-        if (surv) compute_sh(reinterpret_cast<const float4*>(P.sh) + (size_t)i * 12, px, py, pz, U.camera_position, colr, colg, colb);
+        if (surv) compute_sh<SH16>(reinterpret_cast<const float4*>(P.sh) + (size_t)i * (SH16 ? 6 : 12), px, py, pz, U.camera_position, colr, colg, colb);
         __syncthreads();
         // ---- decoupled look-back: warp d walks column d of the status vectors, 32 predecessors per step ----
         if (warp < G) {
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_PROJECT_MIN_BLOCKS) k_project
 
     // ---- SH colour of survivors (overlaps the look-back of other chunks) ----
     float colr = 0.f, colg = 0.f, colb = 0.f;
-    if (surv) compute_sh(reinterpret_cast<const float4*>(P.sh) + (size_t)i * 12, px, py, pz, U.camera_position, colr, colg, colb);
+    if (surv) compute_sh<SH16>(reinterpret_cast<const float4*>(P.sh) + (size_t)i * (SH16 ? 6 : 12), px, py, pz, U.camera_position, colr, colg, colb);
 
     // ---- decoupled look-back by warp 0: 32 predecessors per step ----
     if (warp == 0) {
@@ -976,9 +991,13 @@ __global__ void __launch_bounds__(PRE_THREADS, GSB_EMIT_MIN_BLOCKS) k_emit_cull(
 cudaError_t launch_project(const ProjectParams& p, bool debug, cudaStream_t s) {
     if (p.n == 0) return cudaSuccess;
     const unsigned blocks = (p.n + PRE_THREADS - 1) / PRE_THREADS;
-    if (p.route_world > 0) k_project<false, true><<<blocks, PRE_THREADS, 0, s>>>(p);
-    else if (debug) k_project<true, false><<<blocks, PRE_THREADS, 0, s>>>(p);
-    else k_project<false, false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    if (p.sh_half) {  // fp16 SH storage (non-parity)
+        if (p.route_world > 0) k_project<false, true, true><<<blocks, PRE_THREADS, 0, s>>>(p);
+        else if (debug) k_project<true, false, true><<<blocks, PRE_THREADS, 0, s>>>(p);
+        else k_project<false, false, true><<<blocks, PRE_THREADS, 0, s>>>(p);
+    } else if (p.route_world > 0) k_project<false, true, false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else if (debug) k_project<true, false, false><<<blocks, PRE_THREADS, 0, s>>>(p);
+    else k_project<false, false, false><<<blocks, PRE_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -372,6 +372,7 @@ int enqueue_sharded_phase(gsb_ctx* ctx, ShardFrame& F, int phase) {
         pp.cov_a = ctx->cov_a;
         pp.cov_b = ctx->cov_b;
         pp.sh = ctx->sh;
+        pp.sh_half = ctx->scene_sh_half ? 1 : 0;
         pp.n = (uint32_t)ctx->n;
         pp.index_base = (uint32_t)((uint64_t)r * sh->slice);
         pp.ubo = F.ubo;

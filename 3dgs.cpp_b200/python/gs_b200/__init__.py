@@ -37,7 +37,7 @@ ALL_ROWS = 0xFFFFFFFF
 
 EXPORTED_SYMBOLS = [  # every symbol include/gs_b200.h declares
     "gsb_abi_version", "gsb_device_count", "gsb_create", "gsb_destroy", "gsb_last_error",
-    "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers", "gsb_set_tile_cull",
+    "gsb_scene_upload", "gsb_scene_size", "gsb_set_mode", "gsb_set_debug", "gsb_set_timers", "gsb_set_tile_cull", "gsb_set_sh_storage",
     "gsb_reserve_instances", "gsb_render", "gsb_render_async", "gsb_get_stats", "gsb_debug_size",
     "gsb_debug_download", "gsb_sort_pairs", "gsb_sort_pairs32", "gsb_set_graph", "gsb_host_alloc", "gsb_host_free",
     # frame sharding over several GPUs
@@ -104,6 +104,7 @@ lib.gsb_set_mode.argtypes = [_vp, C.c_int]
 lib.gsb_set_debug.argtypes = [_vp, C.c_int]
 lib.gsb_set_timers.argtypes = [_vp, C.c_int]
 lib.gsb_set_tile_cull.argtypes = [_vp, C.c_int]
+lib.gsb_set_sh_storage.argtypes = [_vp, C.c_int]
 lib.gsb_set_graph.argtypes = [_vp, C.c_int]
 lib.gsb_host_alloc.argtypes = [C.POINTER(_vp), C.c_size_t]
 lib.gsb_host_free.argtypes = [_vp]
@@ -317,6 +318,10 @@ class Context:
     def set_tile_cull(self, level=1):
         """gsb_set_tile_cull: 0 reference lists, 1 (True) exact per-tile instance culling, 2 coarse 4x4-tile bins."""
         self._ck(lib.gsb_set_tile_cull(self.h, int(level)))
+
+    def set_sh_storage(self, half=True):
+        """gsb_set_sh_storage: fp16 SH coefficients from the next upload on (NOT a parity mode)."""
+        self._ck(lib.gsb_set_sh_storage(self.h, int(half)))
 
     def set_timers(self, on=True):
         self._ck(lib.gsb_set_timers(self.h, int(on)))

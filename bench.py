@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--workload", default=None)
     ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sh16", action="store_true", help="gsb_set_sh_storage(1): fp16 SH coefficients -- NOT a parity mode, never the default")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 extra workload measured at --gpus 4 / 8")
     ap.add_argument("--tile-cull", type=int, default=2, help="gsb_set_tile_cull level: 0 reference lists, 1 exact per-tile instance culling, 2 coarse bins (image bit-identical in all three)")
     args = ap.parse_args()
@@ -270,6 +271,8 @@ def main():
         ctx = g.Context(local_rank)
     ctx.set_mode(g.MODE_EXACT if args.mode == "exact" else g.MODE_FAST)
     ctx.set_tile_cull(int(args.tile_cull))
+    if args.sh16:
+        ctx.set_sh_storage(True)
 
     env = dict(g=g, torch=torch, dist=dist, dev=dev, rank=rank, world=world, local_rank=local_rank, ctx=ctx, args=args)
     out = measure(env, wl_name, wl, args.steps, max(3, args.warmup), headline=True)
@@ -499,7 +502,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
     traffic = None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (headline workload, N = 1)
         tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-        traffic = tj["dram_bytes_per_launch"].get(dom) if (headline and not sharded) else None
+        traffic = (tj["dram_bytes_per_launch"].get(dom) or tj["dram_bytes_per_launch"].get(dom + "2")) if (headline and not sharded) else None
     except Exception:
         pass
     roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
@@ -513,7 +516,7 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {**bench_config(wl_name, wl),
                    "instances_M": M, "instances_aabb": float(np.mean(aabb_acc)), "tile_cull": int(args.tile_cull), "visible": NV,
-                   "sort_passes": passes, "blend_mode": args.mode, "output": "BGRA8", "scene_load_s": t_load,
+                   "sort_passes": passes, "blend_mode": args.mode, "sh_storage": "fp16 (NON-PARITY)" if args.sh16 else "fp32", "output": "BGRA8", "scene_load_s": t_load,
                    "l2": "inputs (scene + sort keys, > 1 GB) larger than the 126 MB L2; 8 camera poses alternate; no flush",
                    "parallelism": (f"scene sharded by Gaussian index x{world}, frame by tile-row bands x{world}; survivors and framebuffer "
                                    f"exchanged by stores into peer memory (NVLink), no collective in the frame" if sharded else "single GPU")},

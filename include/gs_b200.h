@@ -146,6 +146,12 @@ const char *gsb_last_error(const gsb_ctx *ctx);
 int gsb_scene_upload(gsb_ctx *ctx, const float *vertices, uint64_t n, gsb_memory mem);
 uint64_t gsb_scene_size(const gsb_ctx *ctx);
 
+/* Storage of the 48 SH coefficients, chosen BEFORE gsb_scene_upload (default 0 = fp32, 192 B per Gaussian).  1 = fp16 (96 B):
+ * NOT a parity mode -- colours come from coefficients rounded to half precision (relative 2^-11), so pixels differ from the
+ * reference / oracle by up to ~1e-3; geometry, culling, instance lists and sort order are unaffected.  It halves the
+ * dominant term of k_project's HBM traffic (SURVEY 8f row 2 "optional fp16 SH storage mode (non-parity)"). */
+int gsb_set_sh_storage(gsb_ctx *ctx, int half_precision);
+
 /* ---- configuration ---- */
 int gsb_set_mode(gsb_ctx *ctx, gsb_mode mode);
 /* debug != 0: keep every intermediate so gsb_debug_download works (extra HBM traffic). */

@@ -249,6 +249,36 @@ def test_coarse_bins_keep_the_image_bit_exact(gs, oracle, ctx, cam, monkeypatch)
             c.close()
 
 
+def test_fp16_sh_storage_is_a_bounded_non_parity_mode(gs, oracle):
+    """gsb_set_sh_storage(1): SH coefficients are stored as fp16 (half of k_project's dominant traffic).  It is flagged
+    non-parity: geometry, culling and instance lists are untouched (same counts, same alpha channel), colours move by the
+    half-precision rounding of the coefficients -- well below 8-bit resolution but above the 1e-4 parity tolerance."""
+    _, vtx, u = scenes.c1()
+    ref = oracle_frame(oracle, vtx, u, 1)
+    c = gs.Context(0)
+    try:
+        c.upload(vtx)
+        exact = c.render(u, gs.FORMAT_RGBA32F)
+        st0 = c.stats()
+        assert np.array_equal(exact, ref["rgba"])
+        c.set_sh_storage(True)
+        c.upload(vtx)
+        for level in (0, 2):
+            c.set_tile_cull(level)
+            img = c.render(u, gs.FORMAT_RGBA32F)
+            st = c.stats()
+            assert (st.num_visible, st.num_instances_aabb) == (st0.num_visible, st0.num_instances_aabb)
+            err = np.abs(img - exact).max()
+            assert 0.0 < err < 4e-3, err
+            assert np.isfinite(img).all() and np.array_equal(img[..., 3], exact[..., 3])
+        c.set_sh_storage(False)  # back to fp32 at the next upload: bit-exact again
+        c.set_tile_cull(0)
+        c.upload(vtx)
+        assert np.array_equal(c.render(u, gs.FORMAT_RGBA32F), ref["rgba"])
+    finally:
+        c.close()
+
+
 def test_device_scan_with_tile_cull(gs, oracle, ctx):
     """With the exact instance cull on, k_emit scans the CULLED per-Gaussian counts: its offsets must partition the
     emitted list exactly (offset[j+1] - offset[j] instances of Gaussian depth_order[j], contiguous, in that order)."""
