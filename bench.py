@@ -535,7 +535,10 @@ def measure(env, wl_name, wl, steps, warmup, headline):
         "kernels": kern,
         "stage_ms": stage,
         "sort_pass_ms_each": pass_each,
+        # keys the instance sort actually moved (with coarse bins: (Gaussian, 4x4-tile block) entries) per second of both sorts;
+        # and the reference's own instance count (AABB tiles, what its 8-pass sort would be given) over the same time
         "sort_keys_per_s": M / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
+        "reference_instances_per_sort_s": float(np.mean(aabb_acc)) / (stage["sort_ms"] * 1e-3) if stage["sort_ms"] > 0 else None,
         # evaluated work, not the algorithmic pair count: one visit = one (warp, record) iteration of the blend's inner loop = 64
         # pixel x Gaussian pairs evaluated (k_blend2: 2 pixels per lane)
         "blend_warp_visits_per_s": VISITS / (stage["render_ms"] * 1e-3) if stage["render_ms"] > 0 else None,
