@@ -624,7 +624,11 @@ __device__ __forceinline__ unsigned long long emit_lookback(unsigned long long* 
 // bound by the latency of the record gather, the look-back and the barriers, not by the expansion: every thread handles
 // EC_IPT consecutive survivors (four independent gathers in flight, a quarter of the chunks / tickets / barriers).
 // ------------------------------------------------------------------------------------------
-constexpr int EC_IPT = 4;
+#ifndef GSB_EMIT_COARSE_IPT
+#define GSB_EMIT_COARSE_IPT 4  // survivors per thread (a multiple of 4: the sorted ids are read 16 B at a time)
+#endif
+constexpr int EC_IPT = GSB_EMIT_COARSE_IPT;
+static_assert(EC_IPT % 4 == 0, "k_emit_coarse reads the sorted ids as uint4");
 constexpr int EC_CHUNK = PRE_THREADS * EC_IPT;
 constexpr int EC_MAXBIG = 32;  // block-expanded Gaussians per chunk; more than that (never seen) fall back to the thread loop
 
@@ -655,8 +659,11 @@ __global__ void __launch_bounds__(PRE_THREADS) k_emit_coarse(const __grid_consta
 
         uint32_t cid[EC_IPT], nt[EC_IPT], bxy[EC_IPT], bwh[EC_IPT], f0[EC_IPT], f1[EC_IPT];
         if (j0 + EC_IPT <= nv) {
-            const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(P.sorted_cid + j0));
-            cid[0] = c4.x, cid[1] = c4.y, cid[2] = c4.z, cid[3] = c4.w;
+#pragma unroll
+            for (int k = 0; k < EC_IPT; k += 4) {
+                const uint4 c4 = __ldg(reinterpret_cast<const uint4*>(P.sorted_cid + j0 + k));
+                cid[k] = c4.x, cid[k + 1] = c4.y, cid[k + 2] = c4.z, cid[k + 3] = c4.w;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < EC_IPT; k++) cid[k] = j0 + k < nv ? __ldg(P.sorted_cid + j0 + k) : 0u;
