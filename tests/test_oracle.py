@@ -247,3 +247,50 @@ def test_parallel_sort_scan_are_the_serial_ones(oracle, threads):
         assert np.array_equal(scan, np.cumsum(tiles.astype(np.uint64)).astype(np.uint32))
     finally:
         oracle.set_num_threads(max(1, len(__import__("os").sched_getaffinity(0))))
+
+
+@pytest.mark.parametrize("cam,shift", [("c1", 2), ("odd_size", 2), ("inside", 2), ("wide", 1)])
+def test_coarse_bin_model_reproduces_every_tile_list(gs, oracle, cam, shift):
+    """The claim behind gsb_set_tile_cull level 2, checked on the oracle's own buffers (no GPU): emit one entry per
+    (Gaussian, block of 2^shift x 2^shift tiles) in depth order with the mask of the block's tiles inside the Gaussian's
+    tile AABB, sort the entries stably by block id, and let every tile keep the entries of its block whose mask has its
+    bit -- that is exactly the tile's own (depth, index)-ordered list of the reference's 64-bit key sort."""
+    _, vtx, _ = scenes.c1(n=3000)
+    u = scenes.camera(cam)
+    f = oracle.render_frame(vtx, oracle.cov3d(vtx), u)
+    tiles_x, tiles_y = f["tiles_x"], f["tiles_y"]
+    bins_x = (tiles_x + (1 << shift) - 1) >> shift
+    aabb = f["attr"]["aabb"].astype(np.int64)
+    depth_bits = f["attr"]["depth"].view(np.uint32).astype(np.uint64)
+    live = np.nonzero(f["tiles"])[0]
+    order = live[np.argsort(depth_bits[live], kind="stable")]  # the Gaussian-level sort: (depth bits, index)
+    keys, vals = [], []
+    for i in order:  # k_emit_coarse: block id | mask << 16, x outer / y inner
+        x0, y0, x1, y1 = aabb[i]
+        for bx in range(x0 >> shift, ((x1 - 1) >> shift) + 1):
+            for by in range(y0 >> shift, ((y1 - 1) >> shift) + 1):
+                m = 0
+                for ly in range(1 << shift):
+                    for lx in range(1 << shift):
+                        tx, ty = (bx << shift) + lx, (by << shift) + ly
+                        if x0 <= tx < x1 and y0 <= ty < y1:
+                            m |= 1 << ((ly << shift) | lx)
+                assert m != 0
+                keys.append((bx + by * bins_x) | (m << 16))
+                vals.append(i)
+    keys, vals = np.array(keys, np.uint64), np.array(vals, np.int64)
+    perm = np.argsort(keys & np.uint64(0xFFFF), kind="stable")  # the instance sort looks at the low 16 bits only
+    keys, vals = keys[perm], vals[perm]
+    blocks = (keys & np.uint64(0xFFFF)).astype(np.int64)
+    ref_tile = (f["keys"] >> np.uint64(32)).astype(np.int64)
+    for ty in range(tiles_y):
+        for tx in range(tiles_x):
+            t = tx + ty * tiles_x
+            want = f["vals"][ref_tile == t].astype(np.int64)  # the reference's list of this tile, in sorted order
+            sel = blocks == (tx >> shift) + (ty >> shift) * bins_x
+            bit = 16 + (((ty & ((1 << shift) - 1)) << shift) | (tx & ((1 << shift) - 1)))
+            got = vals[sel][((keys[sel] >> np.uint64(bit)) & np.uint64(1)).astype(bool)]
+            assert np.array_equal(got, want), (cam, tx, ty)
+    # and the entry count the GPU test pins: (Gaussian, block) pairs of the AABBs
+    nb = ((((aabb[live, 2] - 1) >> shift) - (aabb[live, 0] >> shift) + 1) * (((aabb[live, 3] - 1) >> shift) - (aabb[live, 1] >> shift) + 1)).sum()
+    assert len(keys) == nb
